@@ -1,0 +1,180 @@
+// ORACLE (test infrastructure, NOT product code): C entry points over the CPU restatement, loaded
+// with ctypes by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// only.  Parity status: PARITY UNPINNED at the prover boundary (no golden vectors exist in the
+// reference) -- pinned by Poseidon's published KAT, arithmetic identities and
+// prover<->verifier round trips.
+#include "stark.hpp"
+#include "air_modular.hpp"
+#include "air_g1.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <sstream>
+
+using namespace orc;
+namespace orc { FieldParams g_field; }
+
+enum { AIR_MODULAR = 0, AIR_FQ_EXP = 1, AIR_G1_EXP = 2, AIR_G2_EXP = 3, AIR_FQ12_EXP = 4, AIR_FQ12_EXP_U64 = 5 };
+
+struct OrcConfig { uint32_t security_bits, num_challenges, rate_bits, cap_height, pow_bits, fri_arity_bits, fri_final_poly_bits, num_query_rounds; uint64_t coset_shift; };
+static StarkConfig to_cfg(const OrcConfig* c) {
+  StarkConfig s;
+  if (c) { s.security_bits = c->security_bits; s.num_challenges = c->num_challenges; s.rate_bits = c->rate_bits; s.cap_height = c->cap_height; s.pow_bits = c->pow_bits;
+           s.arity_bits = c->fri_arity_bits; s.final_poly_bits = c->fri_final_poly_bits; s.num_query_rounds = c->num_query_rounds; }
+  return s;
+}
+struct AirHandle { int id; size_t num_io; std::unique_ptr<Air> air; };
+static ProverDebug g_dbg;
+static std::string g_err;
+
+struct G1IoBlob { u64 x_x[4], x_y[4], off_x[4], off_y[4]; u32 exp[8]; u64 out_x[4], out_y[4]; };
+static U256 mk(const u64* p) { U256 r; for (int i = 0; i < 4; i++) r.w[i] = p[i]; return r; }
+
+extern "C" {
+const char* orc_last_error() { return g_err.c_str(); }
+void orc_set_field_params(u64 gen, u64 pow2) { g_field.mult_generator = gen; g_field.pow2_generator = pow2; }
+void orc_poseidon(u64* st) { GF s[12]; for (int i = 0; i < 12; i++) s[i] = GF(st[i]); poseidon(s); for (int i = 0; i < 12; i++) st[i] = s[i].v; }
+void orc_hash_or_noop(const u64* in, size_t n, u64* out4) { std::vector<GF> v(n); for (size_t i = 0; i < n; i++) v[i] = GF(in[i]); Hash4 h = hash_or_noop(v.data(), n); for (int i = 0; i < 4; i++) out4[i] = h.e[i].v; }
+void orc_two_to_one(const u64* l, const u64* r, u64* out4) { Hash4 a, b; for (int i = 0; i < 4; i++) { a.e[i] = GF(l[i]); b.e[i] = GF(r[i]); } Hash4 h = two_to_one(a, b); for (int i = 0; i < 4; i++) out4[i] = h.e[i].v; }
+u64 orc_gl_mul(u64 a, u64 b) { return (GF(a) * GF(b)).v; }
+u64 orc_gl_inv(u64 a) { return gl_inv(GF(a)).v; }
+u64 orc_root_of_unity(int logn) { return root_of_unity(logn).v; }
+// in-place FFT of one column (natural order in/out)
+void orc_fft(u64* data, int logn, int inverse) { std::vector<GF> v(size_t(1) << logn); for (size_t i = 0; i < v.size(); i++) v[i] = GF(data[i]); fft_inplace(v, inverse != 0); for (size_t i = 0; i < v.size(); i++) data[i] = v[i].v; }
+// values (ncols x n, column-major) -> coefficients and LDE values (ncols x n<<rate_bits, natural order)
+void orc_commit_columns(const u64* values, size_t ncols, int logn, int rate_bits, int cap_height, u64* coeffs_out, u64* lde_out, u64* cap_out) {
+  size_t n = size_t(1) << logn, L = n << rate_bits;
+  std::vector<std::vector<GF>> cols(ncols, std::vector<GF>(n));
+  for (size_t c = 0; c < ncols; c++) for (size_t i = 0; i < n; i++) cols[c][i] = GF(values[c * n + i]);
+  PolynomialBatch b = PolynomialBatch::from_values(cols, rate_bits, cap_height);
+  if (coeffs_out) for (size_t c = 0; c < ncols; c++) for (size_t i = 0; i < n; i++) coeffs_out[c * n + i] = b.polynomials[c][i].v;
+  if (lde_out) for (size_t c = 0; c < ncols; c++) for (size_t i = 0; i < L; i++) lde_out[c * L + i] = b.get_lde_values(i, 1)[c].v;
+  if (cap_out) for (size_t k = 0; k < b.tree.cap.size(); k++) for (int j = 0; j < 4; j++) cap_out[4 * k + j] = b.tree.cap[k].e[j].v;
+}
+// Merkle tree over row-major leaves; writes the cap and (optionally) the sibling path of `prove_index`.
+void orc_merkle(const u64* leaves, size_t nleaves, size_t width, int cap_height, u64* cap_out, size_t prove_index, u64* path_out) {
+  std::vector<std::vector<GF>> lv(nleaves, std::vector<GF>(width));
+  for (size_t i = 0; i < nleaves; i++) for (size_t j = 0; j < width; j++) lv[i][j] = GF(leaves[i * width + j]);
+  MerkleTree t(std::move(lv), cap_height);
+  for (size_t k = 0; k < t.cap.size(); k++) for (int j = 0; j < 4; j++) cap_out[4 * k + j] = t.cap[k].e[j].v;
+  if (path_out) { auto p = t.prove(prove_index); for (size_t k = 0; k < p.size(); k++) for (int j = 0; j < 4; j++) path_out[4 * k + j] = p[k].e[j].v; }
+}
+// Challenger transcript replay: observe `n_obs` elements then draw `n_out` challenges.
+void orc_challenger(const u64* obs, size_t n_obs, u64* out, size_t n_out) { Challenger ch; for (size_t i = 0; i < n_obs; i++) ch.observe(GF(obs[i])); for (size_t i = 0; i < n_out; i++) out[i] = ch.get().v; }
+
+void* orc_air_create(int id, size_t num_io) {
+  AirHandle* h = new AirHandle{id, num_io, nullptr};
+  switch (id) {
+    case AIR_MODULAR: h->air.reset(new ModularStark()); break;
+    case AIR_G1_EXP: h->air.reset(new G1ExpStark(num_io)); break;
+    default: delete h; g_err = "unsupported air"; return nullptr;
+  }
+  return h;
+}
+void orc_air_destroy(void* p) { delete (AirHandle*)p; }
+size_t orc_air_num_columns(void* p) { return ((AirHandle*)p)->air->num_columns(); }
+size_t orc_air_num_public_inputs(void* p) { return ((AirHandle*)p)->air->num_public_inputs(); }
+size_t orc_air_num_rows(void* p) { AirHandle* h = (AirHandle*)p; return h->id == AIR_MODULAR ? h->num_io : (h->id == AIR_FQ12_EXP_U64 ? 128 : 512) * h->num_io; }
+size_t orc_air_num_permutation_pairs(void* p) { return ((AirHandle*)p)->air->permutation_pairs().size(); }
+size_t orc_air_result_words(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_FQ_EXP: return 4; case AIR_G1_EXP: return 8; case AIR_G2_EXP: return 16; case AIR_FQ12_EXP: case AIR_FQ12_EXP_U64: return 48; } return 0; }
+size_t orc_air_io_size(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_MODULAR: return 64; case AIR_G1_EXP: return sizeof(G1IoBlob); } return 0; }
+
+static std::vector<G1ExpIONative> g1_ios(const void* ios, size_t n) {
+  const G1IoBlob* b = (const G1IoBlob*)ios; std::vector<G1ExpIONative> v(n);
+  for (size_t i = 0; i < n; i++) { v[i].x = {mk(b[i].x_x), mk(b[i].x_y)}; v[i].offset = {mk(b[i].off_x), mk(b[i].off_y)}; memcpy(v[i].exp_val, b[i].exp, 32); v[i].output = {mk(b[i].out_x), mk(b[i].out_y)}; }
+  return v;
+}
+// Trace generation.  out_cols: num_columns x num_rows column-major.  results (optional): per-io chain
+// result (G1: x,y as 8 u64), which the caller may copy into the io blob's output field.
+int orc_generate_trace(void* p, const void* ios, size_t num_io, u64* out_cols, u64* results) {
+  AirHandle* h = (AirHandle*)p;
+  try {
+    Cols cols;
+    if (h->id == AIR_MODULAR) {
+      const u64* b = (const u64*)ios; std::vector<std::array<U256, 2>> in(num_io);
+      for (size_t i = 0; i < num_io; i++) { in[i][0] = mk(b + 8 * i); in[i][1] = mk(b + 8 * i + 4); }
+      cols = static_cast<ModularStark*>(h->air.get())->generate_trace(in);
+    } else if (h->id == AIR_G1_EXP) {
+      std::vector<G1Point> res;
+      cols = static_cast<G1ExpStark*>(h->air.get())->generate_trace(g1_ios(ios, num_io), &res);
+      if (results) for (size_t i = 0; i < num_io; i++) { memcpy(results + 8 * i, res[i].x.w, 32); memcpy(results + 8 * i + 4, res[i].y.w, 32); }
+    } else { g_err = "unsupported air"; return -1; }
+    size_t n = cols[0].size();
+    for (size_t c = 0; c < cols.size(); c++) for (size_t r = 0; r < n; r++) out_cols[c * n + r] = cols[c][r].v;
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -2; }
+}
+int orc_generate_public_inputs(void* p, const void* ios, size_t num_io, u64* out) {
+  AirHandle* h = (AirHandle*)p;
+  std::vector<GF> pi;
+  if (h->id == AIR_MODULAR) return 0;
+  if (h->id == AIR_G1_EXP) pi = static_cast<G1ExpStark*>(h->air.get())->generate_public_inputs(g1_ios(ios, num_io));
+  else { g_err = "unsupported air"; return -1; }
+  for (size_t i = 0; i < pi.size(); i++) out[i] = pi[i].v;
+  return 0;
+}
+// prove: trace is column-major (num_columns x nrows).  On success *proof_out is malloc'd (free with orc_free).
+int orc_prove(void* p, const u64* trace, size_t nrows, const u64* pis, size_t npis, const OrcConfig* c, uint8_t** proof_out, size_t* len_out) {
+  AirHandle* h = (AirHandle*)p;
+  try {
+    if (c && c->coset_shift) g_field.mult_generator = c->coset_shift;
+    size_t nc = h->air->num_columns();
+    std::vector<std::vector<GF>> cols(nc, std::vector<GF>(nrows));
+    for (size_t k = 0; k < nc; k++) for (size_t r = 0; r < nrows; r++) cols[k][r] = GF(trace[k * nrows + r]);
+    std::vector<GF> pi(npis); for (size_t i = 0; i < npis; i++) pi[i] = GF(pis[i]);
+    g_dbg = ProverDebug();
+    Proof proof = prove(*h->air, to_cfg(c), cols, pi, &g_dbg);
+    std::vector<uint8_t> bytes = serialize_proof(proof);
+    *proof_out = (uint8_t*)malloc(bytes.size()); memcpy(*proof_out, bytes.data(), bytes.size()); *len_out = bytes.size();
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -2; }
+}
+void orc_free(void* p) { free(p); }
+// verify: 0 = accepted, 1 = rejected (reason in orc_last_error), <0 = malformed input
+int orc_verify(void* p, const uint8_t* proof, size_t len, const OrcConfig* c) {
+  AirHandle* h = (AirHandle*)p;
+  try {
+    if (c && c->coset_shift) g_field.mult_generator = c->coset_shift;
+    Proof pr = deserialize_proof(proof, len);
+    std::string r = verify_stark_proof(*h->air, pr, to_cfg(c));
+    if (r.empty()) return 0;
+    g_err = r; return 1;
+  } catch (std::exception& e) { g_err = e.what(); return -2; }
+}
+// Evaluate the AIR constraints on the trace rows themselves (no LDE): returns the number of violated
+// (row, constraint) pairs and writes the first one to first_bad[0..1]; num_constraints_out = constraints per row.
+long orc_check_trace(void* p, const u64* trace, size_t nrows, const u64* pis, size_t npis, long* first_bad, size_t* num_constraints_out) {
+  AirHandle* h = (AirHandle*)p;
+  size_t nc = h->air->num_columns();
+  std::vector<GF> pi(npis); for (size_t i = 0; i < npis; i++) pi[i] = GF(pis[i]);
+  long bad = 0; first_bad[0] = first_bad[1] = -1;
+  std::vector<GF> lv(nc), nv(nc);
+  for (size_t r = 0; r < nrows; r++) {
+    size_t rn = (r + 1) % nrows;
+    for (size_t k = 0; k < nc; k++) { lv[k] = GF(trace[k * nrows + r]); nv[k] = GF(trace[k * nrows + rn]); }
+    Consumer<GF> yc({}, r + 1 == nrows ? GF() : GF(1), r == 0 ? GF(1) : GF(), r + 1 == nrows ? GF(1) : GF());
+    std::vector<GF> log; yc.log = &log;
+    h->air->eval(lv.data(), nv.data(), pi.data(), yc);
+    if (num_constraints_out) *num_constraints_out = log.size();
+    for (size_t k = 0; k < log.size(); k++) if (log[k].v) { if (!bad) { first_bad[0] = (long)r; first_bad[1] = (long)k; } bad++; }
+  }
+  return bad;
+}
+// ---- intermediates of the last orc_prove call (for stage-by-stage parity tests) ----
+size_t orc_dbg_num_z() { return g_dbg.z_polys.size(); }
+void orc_dbg_z_polys(u64* out) { size_t n = g_dbg.z_polys.empty() ? 0 : g_dbg.z_polys[0].size(); for (size_t c = 0; c < g_dbg.z_polys.size(); c++) for (size_t i = 0; i < n; i++) out[c * n + i] = g_dbg.z_polys[c][i].v; }
+void orc_dbg_quotient_chunks(u64* out) { size_t n = g_dbg.quotient_chunks.empty() ? 0 : g_dbg.quotient_chunks[0].size(); for (size_t c = 0; c < g_dbg.quotient_chunks.size(); c++) for (size_t i = 0; i < n; i++) out[c * n + i] = g_dbg.quotient_chunks[c][i].v; }
+// challenges: [alphas(nc)] [zeta a,b] [fri_alpha a,b] [perm sets: for chal, for slot: beta,gamma]
+size_t orc_dbg_challenges(u64* out, size_t cap) {
+  std::vector<u64> v; for (auto a : g_dbg.alphas) v.push_back(a.v);
+  v.push_back(g_dbg.zeta.a.v); v.push_back(g_dbg.zeta.b.v); v.push_back(g_dbg.fri_alpha.a.v); v.push_back(g_dbg.fri_alpha.b.v);
+  for (auto& s : g_dbg.perm_sets) for (auto& ch : s) { v.push_back(ch.beta.v); v.push_back(ch.gamma.v); }
+  for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+  return v.size();
+}
+size_t orc_dbg_timings(char* out, size_t cap) {
+  std::ostringstream os; os << "{"; bool first = true;
+  for (auto& kv : g_dbg.timings_ms) { if (!first) os << ","; first = false; os << "\"" << kv.first << "\":" << kv.second; }
+  os << "}"; std::string s = os.str(); if (cap) { snprintf(out, cap, "%s", s.c_str()); } return s.size();
+}
+}
