@@ -1,0 +1,108 @@
+/* C ABI of the B200 prover path for qope/starky-bn254.
+ *
+ * The reference has no FFI: its seam is the Rust generic call
+ *     starky::prover::prove::<F, C, S, D>(stark, &config, trace_poly_values, public_inputs, &mut timing)
+ * made at reference src/curves/g1/exp.rs:818, src/curves/g1/circuit.rs:192, src/curves/g2/exp.rs:870,
+ * src/fields/fq12/exp.rs:671, src/fields/fq/exp.rs:618, src/modular/modular.rs:550 (19 call sites,
+ * SURVEY.md section 8b), preceded by `stark.generate_trace(&inputs)` / `stark.generate_public_inputs(&inputs)`
+ * (e.g. src/curves/g1/exp.rs:816-817).  A generic callback cannot cross to CUDA, so the replacement is
+ * keyed by an AIR identifier.  All functions return 0 on success and a negative code on failure; they
+ * never abort or throw across the boundary.  Plain pointers and sizes only.
+ */
+#ifndef STARKY_BN254_B200_H
+#define STARKY_BN254_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sbn_ctx sbn_ctx;     /* one per GPU / stream; not thread-safe, thread-compatible */
+typedef struct sbn_trace sbn_trace; /* device-resident, column-major trace (Vec<PolynomialValues<F>>) */
+typedef struct sbn_proof sbn_proof; /* StarkProofWithPublicInputs in the canonical wire format */
+
+/* mirrors starky::config::StarkConfig (+ FriConfig); see sbn_config_standard_fast */
+typedef struct {
+  uint32_t security_bits, num_challenges, rate_bits, cap_height, pow_bits, fri_arity_bits, fri_final_poly_bits, num_query_rounds;
+  uint64_t coset_shift; /* 0 or 7: F::coset_shift() of plonky2_field's Goldilocks */
+} sbn_config;
+
+/* AIR identifiers: the `Stark` implementations of the reference */
+enum {
+  SBN_AIR_MODULAR = 0,      /* ModularStark        src/modular/modular.rs:361-537 (num_io = rows) */
+  SBN_AIR_FQ_EXP = 1,       /* FqExpStark          src/fields/fq/exp.rs */
+  SBN_AIR_G1_EXP = 2,       /* G1ExpStark          src/curves/g1/exp.rs:232-742 */
+  SBN_AIR_G2_EXP = 3,       /* G2ExpStark          src/curves/g2/exp.rs */
+  SBN_AIR_FQ12_EXP = 4,     /* Fq12ExpStark        src/fields/fq12/exp.rs */
+  SBN_AIR_FQ12_EXP_U64 = 5  /* Fq12ExpU64Stark     src/fields/fq12_u64/exp_u64.rs */
+};
+
+#define SBN_OK 0
+#define SBN_ERR_INVALID (-1)
+#define SBN_ERR_CUDA (-2)
+#define SBN_ERR_UNSUPPORTED (-3)
+#define SBN_ERR_INTERNAL (-4)
+
+/* Input record of G1ExpStark, replaces `G1ExpIONative` (src/curves/g1/exp.rs:88-93): canonical
+ * 256-bit little-endian coordinates, exponent as 8 u32 limbs (least significant first). */
+typedef struct {
+  uint64_t x_x[4], x_y[4], offset_x[4], offset_y[4];
+  uint32_t exp_val[8];
+  uint64_t output_x[4], output_y[4];
+} sbn_g1_exp_io;
+/* Input record of ModularStark: one row = two canonical Fq residues (src/modular/modular.rs:385-390). */
+typedef struct { uint64_t input0[4], input1[4]; } sbn_modular_io;
+
+/* `cuda_stream` is a cudaStream_t (may be NULL: the library creates its own stream). */
+int sbn_ctx_create(int device, void* cuda_stream, sbn_ctx** out);
+void sbn_ctx_destroy(sbn_ctx* ctx);
+const char* sbn_last_error(const sbn_ctx* ctx); /* ctx may be NULL: last error of a failed sbn_ctx_create */
+int sbn_ctx_synchronize(sbn_ctx* ctx);
+uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx);  /* kernels launched so far through this context */
+uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx);  /* bytes held by the context's caching allocator */
+
+/* StarkConfig::standard_fast_config (every call site, e.g. src/curves/g1/exp.rs:250-253) */
+int sbn_config_standard_fast(sbn_config* out);
+/* `constants(num_io)` of each AIR (e.g. src/curves/g1/exp.rs:6-34) */
+int sbn_air_info(int air, size_t num_io, size_t* num_columns, size_t* num_public_inputs, size_t* num_rows, size_t* io_size,
+                 size_t* result_words, size_t* num_permutation_pairs);
+
+/* K1: `stark.generate_trace(&inputs)` (src/curves/g1/exp.rs:290-318) on the GPU; `ios` is a host array of
+ * num_io input records of the AIR's type. */
+int sbn_trace_generate(sbn_ctx* ctx, int air, const void* ios, size_t num_io, sbn_trace** out);
+/* Host-generated trace path: `cols` is column-major (ncols x nrows), the layout `prove` takes. */
+int sbn_trace_upload(sbn_ctx* ctx, int air, size_t num_io, const uint64_t* cols, size_t ncols, size_t nrows, sbn_trace** out);
+int sbn_trace_download(const sbn_trace* trace, uint64_t* cols_out);
+/* per-io result of the exponentiation chain (`b` on the last row of each block, src/curves/g1/exp.rs:273-281);
+ * result_words u64 per io */
+int sbn_trace_results(const sbn_trace* trace, uint64_t* out);
+void sbn_trace_free(sbn_trace* trace);
+/* `stark.generate_public_inputs(&inputs)` (src/curves/g1/exp.rs:320-327); host-side formatting only */
+int sbn_public_inputs(int air, const void* ios, size_t num_io, uint64_t* out, size_t out_len);
+
+/* K2-K6: `starky::prover::prove` */
+int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,
+              sbn_proof** out);
+/* Canonical little-endian wire format (DESIGN.md "Proof wire format").  Call with buf == NULL to get the length. */
+int sbn_proof_serialize(const sbn_proof* proof, uint8_t* buf, size_t* len);
+/* JSON object of per-phase device milliseconds of the sbn_prove call that produced `proof` */
+int sbn_proof_timings(const sbn_proof* proof, char* buf, size_t cap);
+/* Intermediates kept for stage-by-stage parity tests: which = 0 permutation Z columns (nz x N values),
+ * 1 quotient chunk coefficients (2*num_challenges x N), 2 challenges (alphas, zeta, fri_alpha, permutation sets). */
+int sbn_proof_debug(const sbn_proof* proof, int which, uint64_t* out, size_t cap_words, size_t* written);
+void sbn_proof_free(sbn_proof* proof);
+
+/* Stage entry points (parity tests and micro-benchmarks; host buffers in, host buffers out) */
+int sbn_poseidon_permute(sbn_ctx* ctx, uint64_t* states, size_t n);  /* n states of 12 u64, in place */
+/* PolynomialBatch::from_values: values (ncols x 2^logn, column-major) -> coeffs, LDE (ncols x 2^(logn+rate_bits),
+ * natural order i -> shift*w^i) and Merkle cap (2^cap_height x 4).  Output pointers may be NULL. */
+int sbn_commit_columns(sbn_ctx* ctx, const uint64_t* values, size_t ncols, int logn, int rate_bits, int cap_height,
+                       uint64_t* coeffs_out, uint64_t* lde_out, uint64_t* cap_out);
+/* Device-resident micro-benchmark of the commitment kernels on synthetic data: fills ms[0..2] with the
+ * average milliseconds of (iNTT+LDE, leaf hashing, upper tree levels) over `iters` runs. */
+int sbn_bench_commit(sbn_ctx* ctx, size_t ncols, int logn, int rate_bits, int cap_height, int iters, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

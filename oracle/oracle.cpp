@@ -160,6 +160,28 @@ long orc_check_trace(void* p, const u64* trace, size_t nrows, const u64* pis, si
   }
   return bad;
 }
+// reference src/utils/lookup.rs:60-111 `permuted_cols`
+void orc_permuted_cols(const u64* inputs, const u64* table, size_t n, u64* sorted_out, u64* perm_out) {
+  std::vector<GF> in(n), tb(n), so, pe;
+  for (size_t i = 0; i < n; i++) { in[i] = GF(inputs[i]); tb[i] = GF(table[i]); }
+  permuted_cols(in, tb, so, pe);
+  for (size_t i = 0; i < n; i++) { sorted_out[i] = so[i].v; perm_out[i] = pe[i].v; }
+}
+// AIR constraints folded by the consumer at one evaluation point (base field), for unit parity tests.
+int orc_eval_constraints(void* p, const u64* lv, const u64* nv, const u64* pis, size_t npis, const u64* alphas, size_t nalpha, u64 z_last, u64 l_first,
+                         u64 l_last, u64* out, size_t* count) {
+  AirHandle* h = (AirHandle*)p;
+  size_t nc = h->air->num_columns();
+  std::vector<GF> l(nc), n(nc), pi(npis), al(nalpha);
+  for (size_t i = 0; i < nc; i++) { l[i] = GF(lv[i]); n[i] = GF(nv[i]); }
+  for (size_t i = 0; i < npis; i++) pi[i] = GF(pis[i]);
+  for (size_t i = 0; i < nalpha; i++) al[i] = GF(alphas[i]);
+  Consumer<GF> yc(al, GF(z_last), GF(l_first), GF(l_last));
+  h->air->eval(l.data(), n.data(), pi.data(), yc);
+  for (size_t i = 0; i < nalpha; i++) out[i] = yc.accs[i].v;
+  if (count) *count = yc.count;
+  return 0;
+}
 // ---- intermediates of the last orc_prove call (for stage-by-stage parity tests) ----
 size_t orc_dbg_num_z() { return g_dbg.z_polys.size(); }
 void orc_dbg_z_polys(u64* out) { size_t n = g_dbg.z_polys.empty() ? 0 : g_dbg.z_polys[0].size(); for (size_t c = 0; c < g_dbg.z_polys.size(); c++) for (size_t i = 0; i < n; i++) out[c * n + i] = g_dbg.z_polys[c][i].v; }

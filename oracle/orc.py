@@ -196,3 +196,34 @@ def dbg_timings():
     buf = C.create_string_buffer(4096)
     lib().orc_dbg_timings(buf, C.c_size_t(4096))
     return json.loads(buf.value.decode())
+
+
+def permuted_cols(inputs, table):
+    i = np.ascontiguousarray(inputs, dtype=np.uint64)
+    t = np.ascontiguousarray(table, dtype=np.uint64)
+    so, pe = np.zeros_like(i), np.zeros_like(i)
+    lib().orc_permuted_cols(_p(i), _p(t), C.c_size_t(len(i)), _p(so), _p(pe))
+    return so, pe
+
+
+def eval_constraints(air, lv, nv, pis, alphas, z_last, l_first, l_last):
+    lv, nv = np.ascontiguousarray(lv, dtype=np.uint64), np.ascontiguousarray(nv, dtype=np.uint64)
+    pis = np.ascontiguousarray(pis, dtype=np.uint64)
+    al = np.ascontiguousarray(alphas, dtype=np.uint64)
+    out = np.zeros(len(al), dtype=np.uint64)
+    cnt = C.c_size_t()
+    lib().orc_eval_constraints(C.c_void_p(air.h), _p(lv), _p(nv), _p(pis), C.c_size_t(air.num_public_inputs), _p(al), C.c_size_t(len(al)),
+                               C.c_uint64(z_last), C.c_uint64(l_first), C.c_uint64(l_last), _p(out), C.byref(cnt))
+    return out, cnt.value
+
+
+def check_trace(air, trace, pis):
+    """Number of (row, constraint) pairs violated by the trace itself, first violation, constraints per row."""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    pis = np.ascontiguousarray(pis, dtype=np.uint64)
+    fb = (C.c_long * 2)()
+    nc = C.c_size_t()
+    L = lib()
+    L.orc_check_trace.restype = C.c_long
+    bad = L.orc_check_trace(C.c_void_p(air.h), _p(trace), C.c_size_t(trace.shape[1]), _p(pis), C.c_size_t(len(pis)), fb, C.byref(nc))
+    return bad, (fb[0], fb[1]), nc.value

@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference's prover surface for the B200 path.
+
+The reference is Rust (`stark.generate_trace(&inputs)`, `stark.generate_public_inputs(&inputs)`,
+`prove::<F, C, S, D>(stark, &config, trace, public_inputs, &mut timing)` -- reference
+src/curves/g1/exp.rs:811-826); no Rust toolchain exists in this image, so this module is the thin
+Python binding over the C ABI (`include/starky_bn254_b200.h`) with the same names and argument
+meaning.  There is NO CPU fallback: importing works anywhere, but every compute call raises unless
+the CUDA library is built and a GPU is present.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import synthetic  # noqa: F401  (seeded inputs, shared by tests and bench)
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libstarkybn254_b200.so")
+
+AIR_MODULAR, AIR_FQ_EXP, AIR_G1_EXP, AIR_G2_EXP, AIR_FQ12_EXP, AIR_FQ12_EXP_U64 = range(6)
+
+
+class SbnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[sbn error {code}] {msg}")
+        self.code = code
+
+
+class StarkConfig(C.Structure):
+    """starky::config::StarkConfig (+ FriConfig).  `standard_fast_config` is what every reference call
+    site uses (reference src/curves/g1/exp.rs:250-253)."""
+    _fields_ = [(n, C.c_uint32) for n in ("security_bits", "num_challenges", "rate_bits", "cap_height", "pow_bits",
+                                          "fri_arity_bits", "fri_final_poly_bits", "num_query_rounds")] + [("coset_shift", C.c_uint64)]
+
+    @staticmethod
+    def standard_fast_config(num_columns=None, num_public_inputs=None):
+        cfg = StarkConfig()
+        rc = lib().sbn_config_standard_fast(C.byref(cfg))
+        if rc != 0:
+            raise SbnError(rc, "sbn_config_standard_fast failed")
+        return cfg
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; fails loudly if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, u64p = C.c_void_p, C.c_size_t, C.c_void_p
+        L.sbn_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+        L.sbn_ctx_destroy.argtypes = [vp]
+        L.sbn_last_error.restype = C.c_char_p
+        L.sbn_last_error.argtypes = [vp]
+        L.sbn_ctx_synchronize.argtypes = [vp]
+        L.sbn_ctx_launch_count.restype = C.c_uint64
+        L.sbn_ctx_launch_count.argtypes = [vp]
+        L.sbn_ctx_device_bytes.restype = C.c_uint64
+        L.sbn_ctx_device_bytes.argtypes = [vp]
+        L.sbn_config_standard_fast.argtypes = [vp]
+        L.sbn_air_info.argtypes = [C.c_int, sz] + [C.POINTER(sz)] * 6
+        L.sbn_trace_generate.argtypes = [vp, C.c_int, vp, sz, C.POINTER(vp)]
+        L.sbn_trace_upload.argtypes = [vp, C.c_int, sz, u64p, sz, sz, C.POINTER(vp)]
+        L.sbn_trace_download.argtypes = [vp, u64p]
+        L.sbn_trace_results.argtypes = [vp, u64p]
+        L.sbn_trace_free.argtypes = [vp]
+        L.sbn_public_inputs.argtypes = [C.c_int, vp, sz, u64p, sz]
+        L.sbn_prove.argtypes = [vp, vp, vp, u64p, sz, C.POINTER(vp)]
+        L.sbn_proof_serialize.argtypes = [vp, vp, C.POINTER(sz)]
+        L.sbn_proof_timings.argtypes = [vp, C.c_char_p, sz]
+        L.sbn_proof_debug.argtypes = [vp, C.c_int, u64p, sz, C.POINTER(sz)]
+        L.sbn_proof_free.argtypes = [vp]
+        L.sbn_poseidon_permute.argtypes = [vp, u64p, sz]
+        L.sbn_commit_columns.argtypes = [vp, u64p, sz, C.c_int, C.c_int, C.c_int, u64p, u64p, u64p]
+        L.sbn_bench_commit.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One per GPU (sbn_ctx).  `stream` may be a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        rc = lib().sbn_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc != 0:
+            raise SbnError(rc, lib().sbn_last_error(None).decode())
+
+    def check(self, rc):
+        if rc != 0:
+            raise SbnError(rc, lib().sbn_last_error(self.h).decode())
+
+    def synchronize(self):
+        self.check(lib().sbn_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().sbn_ctx_launch_count(self.h))
+
+    @property
+    def device_bytes(self):
+        return int(lib().sbn_ctx_device_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().sbn_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stage entry points (parity tests / micro-benchmarks) ----
+    def poseidon_permute(self, states):
+        s = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 12).copy()
+        self.check(lib().sbn_poseidon_permute(self.h, _ptr(s), s.shape[0]))
+        return s
+
+    def commit_columns(self, values, rate_bits=1, cap_height=4, want_lde=True):
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        ncols, n = values.shape
+        logn = int(n).bit_length() - 1
+        coeffs = np.zeros_like(values)
+        lde = np.zeros((ncols, n << rate_bits), dtype=np.uint64) if want_lde else None
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        self.check(lib().sbn_commit_columns(self.h, _ptr(values), ncols, logn, rate_bits, cap_height, _ptr(coeffs),
+                                            _ptr(lde) if want_lde else None, _ptr(cap)))
+        return coeffs, lde, cap
+
+    def bench_commit(self, ncols, logn, rate_bits=1, cap_height=4, iters=3):
+        ms = (C.c_float * 3)()
+        self.check(lib().sbn_bench_commit(self.h, ncols, logn, rate_bits, cap_height, iters, ms))
+        return {"ntt_lde_ms": ms[0], "leaf_hash_ms": ms[1], "tree_ms": ms[2]}
+
+
+class Trace:
+    """Device-resident column-major trace (`Vec<PolynomialValues<F>>` of the reference)."""
+
+    def __init__(self, ctx, handle, stark):
+        self.ctx, self.h, self.stark = ctx, handle, stark
+
+    def download(self):
+        out = np.zeros((self.stark.num_columns, self.stark.num_rows), dtype=np.uint64)
+        self.ctx.check(lib().sbn_trace_download(self.h, _ptr(out)))
+        return out
+
+    def results(self):
+        out = np.zeros((self.stark.num_io, max(self.stark.result_words, 1)), dtype=np.uint64)
+        self.ctx.check(lib().sbn_trace_results(self.h, _ptr(out)))
+        return out[:, :self.stark.result_words]
+
+    def free(self):
+        if self.h:
+            lib().sbn_trace_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class StarkProofWithPublicInputs:
+    """Proof in the canonical wire format (DESIGN.md "Proof wire format")."""
+
+    def __init__(self, ctx, handle):
+        n = C.c_size_t()
+        ctx.check(lib().sbn_proof_serialize(handle, None, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        ctx.check(lib().sbn_proof_serialize(handle, buf, C.byref(n)))
+        self.bytes = buf.raw[:n.value]
+        tb = C.create_string_buffer(4096)
+        lib().sbn_proof_timings(handle, tb, 4096)
+        self.timings = json.loads(tb.value.decode() or "{}")
+        self._debug = {}
+        for which, name in ((0, "z_polys"), (1, "quotient_chunks"), (2, "challenges")):
+            w = C.c_size_t()
+            lib().sbn_proof_debug(handle, which, None, 0, C.byref(w))
+            arr = np.zeros(w.value, dtype=np.uint64)
+            if w.value:
+                lib().sbn_proof_debug(handle, which, _ptr(arr), w.value, C.byref(w))
+            self._debug[name] = arr
+        lib().sbn_proof_free(handle)
+
+    def to_bytes(self):
+        return self.bytes
+
+    def debug(self, name):
+        return self._debug[name]
+
+
+class _Stark:
+    AIR = None
+
+    def __init__(self, num_io, ctx=None):
+        self.num_io = num_io
+        self.ctx = ctx
+        v = [C.c_size_t() for _ in range(6)]
+        rc = lib().sbn_air_info(self.AIR, num_io, *[C.byref(x) for x in v])
+        if rc != 0:
+            raise SbnError(rc, lib().sbn_last_error(None).decode())
+        (self.num_columns, self.num_public_inputs, self.num_rows, self.io_size, self.result_words, self.num_permutation_pairs) = [x.value for x in v]
+
+    def config(self):
+        return StarkConfig.standard_fast_config(self.num_columns, self.num_public_inputs)
+
+    def _ctx(self, ctx):
+        c = ctx or self.ctx
+        if c is None:
+            raise ValueError("a Context is required")
+        return c
+
+    def generate_trace(self, inputs: bytes, ctx=None):
+        """K1 on the GPU.  `inputs` = num_io packed input records (see include/starky_bn254_b200.h)."""
+        c = self._ctx(ctx)
+        if len(inputs) != self.io_size * self.num_io:
+            raise ValueError("inputs has the wrong length")
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(inputs), len(inputs))
+        c.check(lib().sbn_trace_generate(c.h, self.AIR, buf, self.num_io, C.byref(h)))
+        return Trace(c, h, self)
+
+    def upload_trace(self, cols, ctx=None):
+        """Host-generated trace path (column-major (num_columns, num_rows) uint64)."""
+        c = self._ctx(ctx)
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        h = C.c_void_p()
+        c.check(lib().sbn_trace_upload(c.h, self.AIR, self.num_io, _ptr(cols), cols.shape[0], cols.shape[1], C.byref(h)))
+        return Trace(c, h, self)
+
+    def generate_public_inputs(self, inputs: bytes):
+        out = np.zeros(max(self.num_public_inputs, 1), dtype=np.uint64)
+        buf = C.create_string_buffer(bytes(inputs), len(inputs))
+        rc = lib().sbn_public_inputs(self.AIR, buf, self.num_io, _ptr(out), self.num_public_inputs)
+        if rc != 0:
+            raise SbnError(rc, lib().sbn_last_error(None).decode())
+        return out[:self.num_public_inputs]
+
+
+class ModularStark(_Stark):
+    """reference src/modular/modular.rs:361-537 (rows = num_io)."""
+    AIR = AIR_MODULAR
+
+
+class G1ExpStark(_Stark):
+    """reference src/curves/g1/exp.rs:232-742."""
+    AIR = AIR_G1_EXP
+
+
+def prove(stark, config, trace, public_inputs, timing=None):
+    """`starky::prover::prove(stark, &config, trace_poly_values, public_inputs, &mut timing)` on the GPU."""
+    ctx = trace.ctx
+    pi = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+    h = C.c_void_p()
+    ctx.check(lib().sbn_prove(ctx.h, C.byref(config), trace.h, _ptr(pi), len(pi), C.byref(h)))
+    proof = StarkProofWithPublicInputs(ctx, h)
+    if timing is not None:
+        timing.update(proof.timings)
+    return proof

@@ -1,0 +1,323 @@
+// K5 building blocks: per-point evaluation of the reference's constraint programs
+// (`Stark::eval_packed_generic` and the gadget `eval_*` functions), restated for a
+// thread-per-LDE-point kernel over column-major LDE data.
+//
+// The starky consumer folds constraints as acc = acc*alpha + c, so only the ORDER and
+// the values of the emitted constraints matter.  The AIR is cut into "segments" (one kernel each);
+// a segment folds its own constraints with Horner and the caller combines
+// acc <- acc * alpha^m + S (m = #constraints in the segment), which is the same field element.
+//
+// Every function cites the reference function it replays.  Column indices are relative to the AIR
+// row; `lv(c)` / `nv(c)` read column c at the local / next LDE point.
+#pragma once
+#include "gl.cuh"
+
+struct F {
+  u64 v;
+  HD F() : v(0) {}
+  HD explicit F(u64 x) : v(x) {}
+};
+HD F operator+(F a, F b) { return F(gl_add(a.v, b.v)); }
+HD F operator-(F a, F b) { return F(gl_sub(a.v, b.v)); }
+HD F operator*(F a, F b) { return F(gl_mul(a.v, b.v)); }
+HD F operator-(F a) { return F(gl_neg(a.v)); }
+
+#define SBN_MAX_CHALLENGES 2
+
+// Evaluation context of one LDE point (plays the role of StarkEvaluationVars + ConstraintConsumer).
+struct QPoint {
+  const u64* lp;   // &lde[0][local point]
+  const u64* np;   // &lde[0][next point]
+  size_t stride;   // distance between consecutive columns
+  const u64* pi;   // public inputs
+  F z_last, l_first, l_last;
+  F alpha[SBN_MAX_CHALLENGES];
+  F acc[SBN_MAX_CHALLENGES];
+  HD F lv(int c) const { return F(lp[(size_t)c * stride]); }
+  HD F nv(int c) const { return F(np[(size_t)c * stride]); }
+  HD void constraint(F c) {
+#pragma unroll
+    for (int k = 0; k < SBN_MAX_CHALLENGES; k++) acc[k] = acc[k] * alpha[k] + c;
+  }
+  HD void transition(F c) { constraint(c * z_last); }
+  HD void first_row(F c) { constraint(c * l_first); }
+  HD void last_row(F c) { constraint(c * l_last); }
+  // n consecutive constraints whose value is identically zero (acc <- acc * alpha^n)
+  HD void zeros(int n) {
+    for (int i = 0; i < n; i++) {
+#pragma unroll
+      for (int k = 0; k < SBN_MAX_CHALLENGES; k++) acc[k] = acc[k] * alpha[k];
+    }
+  }
+};
+
+#define BN254_LIMB_LIST {64839, 55420, 35862, 15392, 51853, 26737, 27281, 38785, 22621, 33153, 17846, 47184, 41001, 57649, 20082, 12388}
+#define GL_INV_65536 18446462594437939201ULL   // reference src/modular/addcy.rs:13
+#define AUX_COEFF_ABS_MAX_U (1ULL << 29)       // reference src/modular/modular.rs:28
+
+HD u64 bn254_limb(int i) {
+  const u32 m[16] = BN254_LIMB_LIST;
+  return m[i];
+}
+
+// Description of the input polynomial of a modular gadget:  in(x) = s1*A(x)*B(x) - s2*C(x)*D(x) - E(x)
+// with A..E 16-limb columns (local row).  a/b/c/d/e are arrays of 16 values already loaded.
+struct ModInput {
+  const F* A; const F* B; u64 s1;
+  const F* C; const F* D; u64 s2;   // C == nullptr: no second product
+  const F* E;                        // nullptr: none.  16 coefficients.
+  bool e_is_sum;                     // E given as E1 + E2 (E2 below)
+  const F* E2;
+};
+HD F mod_input_coeff(const ModInput& in, int k) {
+  F acc;
+  int lo = k > 15 ? k - 15 : 0, hi = k < 15 ? k : 15;
+  for (int i = lo; i <= hi; i++) acc = acc + in.A[i] * in.B[k - i];
+  if (in.s1 != 1) acc = acc * F(in.s1);
+  if (in.C) {
+    F acc2;
+    for (int i = lo; i <= hi; i++) acc2 = acc2 + in.C[i] * in.D[k - i];
+    if (in.s2 != 1) acc2 = acc2 * F(in.s2);
+    acc = acc - acc2;
+  }
+  if (in.E && k < 16) { acc = acc - in.E[k]; if (in.E2) acc = acc - in.E2[k]; }
+  return acc;
+}
+
+// reference src/modular/modular.rs:215-230 `eval_modular_op` (incl. `modular_constr_poly` :102-153 and
+// `eval_packed_generic_addcy` addcy.rs:16-58): 33 + 1 + 32 constraints.
+// Columns: output at out_col (16); aux block at aux_col = out_aux_red(16) | quot_abs(17) | lo(31) | hi(31);
+// sign at sign_col.
+HD void eval_modular_op(QPoint& q, F filter, const ModInput& in, const F* output /*16 loaded*/, int aux_col, int sign_col) {
+  const F overflow(1ULL << 16), overflow_inv(GL_INV_65536);
+  // addcy(modulus, out_aux_red, output, is_less_than=[1,0,..,0])
+  F cy;
+  for (int i = 0; i < 16; i++) {
+    F t = cy + F(bn254_limb(i)) + q.lv(aux_col + i) - output[i];
+    q.constraint(filter * t * (overflow - t));
+    cy = t * overflow_inv;
+  }
+  q.zeros(1);                                  // filter * given_cy[0] * (given_cy[0] - 1), given_cy[0] = 1
+  q.constraint(filter * (cy - F(1)));
+  q.zeros(15);                                 // filter * given_cy[i], i >= 1
+  F sign = q.lv(sign_col);
+  q.constraint(filter * (sign * sign - F(1)));
+  // constr_poly[k] = sum_{i+j=k} (sign*quot_abs[i]) * m[j] + output[k] + (x - beta) * aux(x) [k] - input[k]
+  F quot[17];
+  for (int i = 0; i < 17; i++) quot[i] = sign * q.lv(aux_col + 16 + i);
+  const F base(1ULL << 16), offset(AUX_COEFF_ABS_MAX_U);
+  F aux_prev;  // aux_poly[k-1]
+  for (int k = 0; k < 32; k++) {
+    F c;
+    int lo = k > 15 ? k - 15 : 0, hi = k < 16 ? k : 16;
+    for (int i = lo; i <= hi; i++) c = c + quot[i] * F(bn254_limb(k - i));
+    if (k < 16) c = c + output[k];
+    F aux_k;
+    if (k < 31) aux_k = q.lv(aux_col + 33 + k) - offset + base * q.lv(aux_col + 64 + k);
+    // pol_adjoin_root: res[0] = -root*a[0]; res[k] = a[k-1] - root*a[k]
+    c = c + (k == 0 ? -(base * aux_k) : aux_prev - base * aux_k);
+    aux_prev = aux_k;
+    if (k < 31) c = c - mod_input_coeff(in, k);
+    q.constraint(filter * c);
+  }
+}
+
+// reference src/modular/modular_zero.rs:82-120 `eval_modular_zero`: 1 + 32 constraints.
+// aux block at aux_col = quot_abs(17) | lo(31) | hi(31).
+HD void eval_modular_zero(QPoint& q, F filter, const ModInput& in, int aux_col, int sign_col) {
+  F sign = q.lv(sign_col);
+  q.constraint(filter * (sign * sign - F(1)));
+  F quot[17];
+  for (int i = 0; i < 17; i++) quot[i] = sign * q.lv(aux_col + i);
+  const F base(1ULL << 16), offset(AUX_COEFF_ABS_MAX_U);
+  F aux_prev;
+  for (int k = 0; k < 32; k++) {
+    F c;
+    int lo = k > 15 ? k - 15 : 0, hi = k < 16 ? k : 16;
+    for (int i = lo; i <= hi; i++) c = c + quot[i] * F(bn254_limb(k - i));
+    F aux_k;
+    if (k < 31) aux_k = q.lv(aux_col + 17 + k) - offset + base * q.lv(aux_col + 48 + k);
+    c = c + (k == 0 ? -(base * aux_k) : aux_prev - base * aux_k);
+    aux_prev = aux_k;
+    if (k < 31) c = c - mod_input_coeff(in, k);
+    q.constraint(filter * c);
+  }
+}
+
+HD void load16(const QPoint& q, int col, F* out) { for (int i = 0; i < 16; i++) out[i] = q.lv(col + i); }
+HD void load16n(const QPoint& q, int col, F* out) { for (int i = 0; i < 16; i++) out[i] = q.nv(col + i); }
+
+// reference src/utils/lookup.rs:13-34 `eval_lookups`
+HD void eval_lookups(QPoint& q, int col_in, int col_tab) {
+  F local_in = q.lv(col_in), next_tab = q.nv(col_tab), next_in = q.nv(col_in);
+  F d_prev = next_in - local_in, d_tab = next_in - next_tab;
+  q.constraint(d_prev * d_tab);
+  q.last_row(d_tab);
+}
+
+// reference src/utils/flags.rs:136-195 `eval_flags`: 26 constraints.
+HD void eval_flags(QPoint& q, int sf) {
+  const int is_final_c = sf, is_rotate_c = sf + 1, a = sf + 2, b = sf + 3, fbit = sf + 4, bit_c = sf + 5, sl = sf + 6, el = sl + 8;
+  const F one(1);
+  q.first_row(q.lv(a));
+  q.first_row(q.lv(b) - one);
+  F bit = q.lv(bit_c);
+  q.constraint(bit * bit - bit);
+  q.constraint(bit * q.lv(b) - q.lv(fbit));
+  q.constraint(q.lv(is_rotate_c) * q.lv(a));
+  q.constraint(q.lv(is_final_c) * q.lv(is_rotate_c));
+  q.transition(q.lv(a) + q.nv(a) - one);
+  q.transition(q.lv(b) + q.nv(b) - one);
+  F first_limb = q.lv(sl), next_first_limb = q.nv(sl), next_bit = q.nv(bit_c), is_split = q.lv(a), is_final = q.lv(is_final_c);
+  F is_not_final = one - is_final;
+  q.transition(is_not_final * is_split * (first_limb - F(2) * next_first_limb - next_bit));
+  F is_not_split = one - is_split, is_rotate = q.lv(is_rotate_c), nrf = one - is_rotate - is_final;
+  q.transition(is_not_split * (next_bit - bit));
+  q.transition(nrf * is_not_split * (first_limb - next_first_limb));
+  for (int c = sl + 1; c < el; c++) q.transition(is_rotate * (q.nv(c - 1) - q.lv(c)));
+  q.transition(is_rotate * q.nv(el - 1));
+  for (int c = sl + 1; c < el; c++) q.transition(nrf * (q.nv(c) - q.lv(c)));
+}
+
+// reference src/utils/pulse.rs:146-170 `eval_periodic_pulse`: 5 constraints.
+HD void eval_periodic_pulse(QPoint& q, int pulse_col, int start, int period, int first_pulse) {
+  const F one(1);
+  F counter = q.lv(start), witness = q.lv(start + 1), is_reset = q.lv(pulse_col), next_counter = q.nv(start);
+  q.first_row(counter - F((u64)(period - first_pulse - 1)));
+  q.transition((one - is_reset) * (next_counter - counter - one));
+  q.transition(is_reset * next_counter);
+  F delta = counter - F((u64)(period - 1));
+  q.constraint(delta * witness + is_reset - one);
+  q.constraint(delta * is_reset);
+}
+
+// reference src/utils/pulse.rs:45-63 `eval_pulse` with positions = [rows_per_io*i, rows_per_io*i + rows_per_io-1]
+// (reference src/curves/g1/exp.rs:153-163 `get_pulse_positions`): 2 + 4*num_io constraints.
+HD void eval_pulse(QPoint& q, int start, int num_io, int rows_per_io) {
+  const F one(1);
+  F counter = q.lv(start);
+  q.first_row(counter);
+  q.transition(q.nv(start) - counter - one);
+  for (int i = 0; i < 2 * num_io; i++) {
+    u64 pos = (u64)(i >> 1) * rows_per_io + ((i & 1) ? rows_per_io - 1 : 0);
+    F cmp = counter - F(pos);
+    F witness = q.lv(start + 1 + 2 * i), pulse = q.lv(start + 2 + 2 * i);
+    q.constraint(cmp * witness + pulse - one);
+    q.constraint(cmp * pulse);
+  }
+}
+
+// reference src/utils/range_check.rs:49-68 `eval_u16_range_check`: 2*ntargets + 3 constraints.
+HD void eval_u16_range_check(QPoint& q, int start, int ntargets) {
+  for (int i = start + 1; i < start + 1 + 2 * ntargets; i += 2) eval_lookups(q, i, i + 1);
+  F cur = q.lv(start), next = q.nv(start);
+  q.first_row(cur);
+  F incr = next - cur;
+  q.transition(incr * incr - incr);
+  q.last_row(cur - F((1 << 16) - 1));
+}
+
+// reference src/utils/range_check.rs:162-192 `eval_split_u16_range_check`: 5*ntargets + 3 constraints.
+HD void eval_split_u16_range_check(QPoint& q, int main_col, int t0, int ntargets) {
+  for (int i = 0; i < ntargets; i++) {
+    F original = q.lv(t0 + i), lo = q.lv(main_col + 1 + 6 * i), hi = q.lv(main_col + 4 + 6 * i);
+    q.constraint(original - (lo + hi * F(1 << 8)));
+  }
+  for (int i = main_col + 1; i < main_col + 1 + 6 * ntargets; i += 6) { eval_lookups(q, i + 1, i + 2); eval_lookups(q, i + 4, i + 5); }
+  F cur = q.lv(main_col), next = q.nv(main_col);
+  q.first_row(cur);
+  F incr = next - cur;
+  q.transition(incr * incr - incr);
+  q.last_row(cur - F((1 << 8) - 1));
+}
+
+// ---- ModularStark (reference src/modular/modular.rs:440-482), the part after the range check ----
+HD void eval_modular_stark_core(QPoint& q) {
+  F in0[16], in1[16], out[16];
+  load16(q, 0, in0); load16(q, 16, in1); load16(q, 32, out);
+  ModInput in = {in0, in1, 1, nullptr, nullptr, 1, nullptr, false, nullptr};
+  F filter = q.lv(48 + 95 + 1);
+  eval_modular_op(q, filter, in, out, 48, 48 + 95);
+}
+
+// ---- G1 (reference src/curves/g1/muladd.rs) ----
+// G1Output block at column o: lambda(16) new_x(16) new_y(16) aux_zero(79) aux_x(95) aux_y(95) sign_zero sign_x sign_y
+#define G1O_LAMBDA 0
+#define G1O_NEW_X 16
+#define G1O_NEW_Y 32
+#define G1O_AUX_ZERO 48
+#define G1O_AUX_X 127
+#define G1O_AUX_Y 222
+#define G1O_SIGN_ZERO 317
+#define G1O_SIGN_X 318
+#define G1O_SIGN_Y 319
+
+// shared tail of eval_g1_add / eval_g1_double (muladd.rs:199-229 / :317-341)
+HD void eval_g1_tail(QPoint& q, F filter, int o, const F* lambda, const F* x1, const F* x2, const F* y1) {
+  F new_x[16], new_y[16];
+  load16(q, o + G1O_NEW_X, new_x); load16(q, o + G1O_NEW_Y, new_y);
+  // new_x_input = lambda^2 - (x1 + x2)
+  ModInput inx = {lambda, lambda, 1, nullptr, nullptr, 1, x1, true, x2};
+  eval_modular_op(q, filter, inx, new_x, o + G1O_AUX_X, o + G1O_SIGN_X);
+  // new_y_input = lambda * (x1 - new_x) - y1
+  F d[16];
+  for (int i = 0; i < 16; i++) d[i] = x1[i] - new_x[i];
+  ModInput iny = {lambda, d, 1, nullptr, nullptr, 1, y1, false, nullptr};
+  eval_modular_op(q, filter, iny, new_y, o + G1O_AUX_Y, o + G1O_SIGN_Y);
+}
+// reference src/curves/g1/muladd.rs:179-230 `eval_g1_add`: 33 + 66 + 66 constraints.  a at cols 0..31, b at 32..63.
+HD void eval_g1_add(QPoint& q, F filter, int o) {
+  F ax[16], ay[16], bx[16], by[16], lambda[16], dx[16], dy[16];
+  load16(q, 0, ax); load16(q, 16, ay); load16(q, 32, bx); load16(q, 48, by); load16(q, o + G1O_LAMBDA, lambda);
+  for (int i = 0; i < 16; i++) { dx[i] = bx[i] - ax[i]; dy[i] = by[i] - ay[i]; }
+  // zero_pol = lambda * delta_x - delta_y
+  ModInput inz = {lambda, dx, 1, nullptr, nullptr, 1, dy, false, nullptr};
+  eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
+  eval_g1_tail(q, filter, o, lambda, ax, bx, ay);
+}
+// reference src/curves/g1/muladd.rs:291-342 `eval_g1_double`: 165 constraints.
+HD void eval_g1_double(QPoint& q, F filter, int o) {
+  F x[16], y[16], lambda[16];
+  load16(q, 0, x); load16(q, 16, y); load16(q, o + G1O_LAMBDA, lambda);
+  // zero_pol = 2*lambda*y - 3*x*x
+  ModInput inz = {lambda, y, 2, x, x, 3, nullptr, false, nullptr};
+  eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
+  eval_g1_tail(q, filter, o, lambda, x, x, y);
+}
+
+// reference src/curves/g1/exp.rs:340-461: is_final constraint, public-input binding, transitions.
+// 1 + 56*num_io + 192 constraints.  Column map: a(32) b(32) output(320) flags(14) | periodic(2) | pulses(1+4n) | lookups
+HD void eval_g1_exp_core(QPoint& q, int num_io) {
+  const int sf = 24 * 16, out_o = 64, start_pulses = sf + 14 + 2;
+  const F one(1), base(1ULL << 16);
+  F is_add = q.lv(sf + 4), is_double = q.lv(sf + 2), is_final = q.lv(sf), is_not_final = one - is_final;
+  F sum_is_output;
+  for (int i = 1; i < 2 * num_io; i += 2) sum_is_output = sum_is_output + q.lv(start_pulses + 2 + 2 * i);
+  q.constraint(is_final - sum_is_output);
+  // row values the public inputs are compared with (u16 limb pairs -> u32, reference utils.rs:56-63)
+  F v[7][8];
+  for (int g = 0; g < 4; g++) for (int j = 0; j < 8; j++) v[g][j] = q.lv(16 * g + 2 * j) + base * q.lv(16 * g + 2 * j + 1);
+  for (int j = 0; j < 8; j++) { v[5][j] = v[2][j]; v[6][j] = v[3][j]; }
+  for (int j = 0; j < 8; j++) v[4][j] = q.lv(sf + 6 + j);
+  v[4][0] = v[4][0] * F(2) + is_add;
+  for (int i = 0; i < num_io; i++) {
+    F is_in = q.lv(start_pulses + 2 + 4 * i), is_out = q.lv(start_pulses + 4 + 4 * i);
+    const u64* io = q.pi + 56 * i;  // x.x x.y off.x off.y exp out.x out.y
+    // emission order (exp.rs:381-391): x.x, x.y, offset.x, offset.y (input), output.x, output.y (output), exp_val (input)
+    for (int g = 0; g < 4; g++) for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * g + j]) - v[g][j]));
+    for (int g = 5; g < 7; g++) for (int j = 0; j < 8; j++) q.constraint(is_out * (F(io[8 * g + j]) - v[g][j]));
+    for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[32 + j]) - v[4][j]));
+  }
+  // transitions (exp.rs:393-461)
+  F f1 = is_not_final * is_double, f2 = is_not_final * is_add, f3 = is_not_final * (one - is_double - is_add);
+  // is_double: next_a = output.new, next_b = b
+  for (int i = 0; i < 16; i++) q.transition(f1 * (q.nv(i) - q.lv(out_o + G1O_NEW_X + i)));
+  for (int i = 0; i < 16; i++) q.transition(f1 * (q.nv(16 + i) - q.lv(out_o + G1O_NEW_Y + i)));
+  for (int i = 0; i < 32; i++) q.transition(f1 * (q.nv(32 + i) - q.lv(32 + i)));
+  // is_add: next_a = a, next_b = output.new
+  for (int i = 0; i < 32; i++) q.transition(f2 * (q.nv(i) - q.lv(i)));
+  for (int i = 0; i < 16; i++) q.transition(f2 * (q.nv(32 + i) - q.lv(out_o + G1O_NEW_X + i)));
+  for (int i = 0; i < 16; i++) q.transition(f2 * (q.nv(48 + i) - q.lv(out_o + G1O_NEW_Y + i)));
+  // neither: next = current
+  for (int i = 0; i < 64; i++) q.transition(f3 * (q.nv(i) - q.lv(i)));
+}

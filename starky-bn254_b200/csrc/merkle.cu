@@ -1,0 +1,95 @@
+// K3: Poseidon-Goldilocks Merkle commitment over LDE rows.  Replaces plonky2's `MerkleTree::new`
+// with `hash_or_noop` leaves and `two_to_one` nodes (external dependency), reached
+// from the reference through `prove()` (reference src/curves/g1/exp.rs:818).
+//
+// One thread hashes one leaf (= one LDE row across all columns).  The LDE batch is column-major, so
+// the 32 threads of a warp read 32 consecutive u64 of the same column: every load is a fully
+// coalesced 256-byte run and the row never has to be materialised.  Digests are written to the
+// bit-reversed leaf position plonky2 uses (32-byte aligned stores).
+#include "merkle.cuh"
+#include "poseidon.cuh"
+
+__global__ void __launch_bounds__(128) k_leaf_hash(const u64* __restrict__ lde, size_t col_stride, int ncols, int logn, int rate_bits,
+                                                   u64* __restrict__ digests) {
+  const size_t L = size_t(1) << (logn + rate_bits);
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  const u32 b = (u32)(idx >> logn), k = (u32)(idx & ((size_t(1) << logn) - 1));
+  const size_t pos = ((size_t)bitrev32(b, rate_bits) << logn) + bitrev32(k, logn);
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = 0;
+  const u64* p = lde + idx;
+  if (ncols <= 4) {  // hash_or_noop: short rows are copied, not hashed
+#pragma unroll
+    for (int c = 0; c < 4; c++) if (c < ncols) st[c] = p[(size_t)c * col_stride];
+  } else {
+    int c = 0;
+    for (; c + 8 <= ncols; c += 8) {
+      u64 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = p[(size_t)(c + i) * col_stride];
+#pragma unroll
+      for (int i = 0; i < 8; i++) st[i] = v[i];
+      poseidon_permute(st);
+    }
+    if (c < ncols) {
+      u64 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = (c + i < ncols) ? p[(size_t)(c + i) * col_stride] : 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) if (c + i < ncols) st[i] = v[i];
+      poseidon_permute(st);
+    }
+  }
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + pos * 4);
+  d[0] = make_ulonglong2(st[0], st[1]);
+  d[1] = make_ulonglong2(st[2], st[3]);
+}
+
+__global__ void __launch_bounds__(128) k_merkle_level(const u64* __restrict__ child, u64* __restrict__ parent, size_t nparents) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nparents) return;
+  const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);
+  ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2], b1 = c[3];
+  u64 st[12] = {a0.x, a0.y, a1.x, a1.y, b0.x, b0.y, b1.x, b1.y, 0, 0, 0, 0};
+  poseidon_permute(st);
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(parent + i * 4);
+  d[0] = make_ulonglong2(st[0], st[1]);
+  d[1] = make_ulonglong2(st[2], st[3]);
+}
+
+void merkle_alloc(sbn_ctx* ctx, DevMerkleTree* t, size_t nleaves, int cap_height) {
+  SBN_REQUIRE(nleaves >= (size_t(1) << cap_height), "merkle: fewer leaves than cap entries");
+  t->nleaves = nleaves; t->cap_height = cap_height;
+  t->level_off.clear();
+  size_t off = 0;
+  for (size_t n = nleaves; n >= (size_t(1) << cap_height); n >>= 1) { t->level_off.push_back(off); off += n * 4; if (n == 1) break; }
+  t->digests = DevBuf<u64>(ctx, off);
+}
+
+void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t) {
+  size_t n = t->nleaves;
+  for (int l = 0; l + 1 < t->num_levels(); l++) {
+    size_t np = n >> 1;
+    k_merkle_level<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(t->digests + t->level_off[l], t->digests + t->level_off[l + 1], np);
+    LAUNCH_CHECK(ctx);
+    n = np;
+  }
+  t->cap.resize((size_t(4)) << t->cap_height);
+  CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->digests + t->level_off.back(), t->cap.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void merkle_leaf_hash_only(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int rate_bits, DevMerkleTree* t) {
+  size_t L = size_t(1) << (logn + rate_bits);
+  k_leaf_hash<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(lde, L, ncols, logn, rate_bits, t->digests);
+  LAUNCH_CHECK(ctx);
+}
+
+void merkle_commit_lde(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int rate_bits, int cap_height, DevMerkleTree* out) {
+  size_t L = size_t(1) << (logn + rate_bits);
+  merkle_alloc(ctx, out, L, cap_height);
+  merkle_leaf_hash_only(ctx, lde, ncols, logn, rate_bits, out);
+  merkle_build_from_leaf_digests(ctx, out);
+}

@@ -1,0 +1,506 @@
+// Host orchestration of `starky::prover::prove` (external dependency of the reference; SURVEY.md
+// sections 3.3 and App. B) over the CUDA kernel families K2-K6, plus the extern "C" boundary declared in
+// include/starky_bn254_b200.h.  The Fiat-Shamir challenger runs on the host (a few dozen Poseidon
+// permutations per proof); everything that touches trace-sized data runs on the device.
+#include "../../include/starky_bn254_b200.h"
+#include "common.cuh"
+#include "air.cuh"
+#include "ntt.cuh"
+#include "merkle.cuh"
+#include "quotient.cuh"
+#include "zpoly.cuh"
+#include "fri.cuh"
+#include "tracegen.cuh"
+#include "poseidon.cuh"
+#include <map>
+#include <memory>
+#include <sstream>
+
+// ------------------------------------------------------------------------------------------------
+// plonky2::iop::challenger::Challenger: duplex sponge in overwrite mode; challenges
+// are popped from the END of the 8-element output buffer.
+struct Challenger {
+  u64 st[12]; std::vector<u64> in, out;
+  Challenger() { memset(st, 0, sizeof st); }
+  void duplex() {
+    for (size_t i = 0; i < in.size(); i++) st[i] = in[i];
+    in.clear();
+    poseidon_permute(st);
+    out.assign(st, st + 8);
+  }
+  void observe(u64 x) { out.clear(); in.push_back(x); if (in.size() == 8) duplex(); }
+  void observe_n(const u64* p, size_t n) { for (size_t i = 0; i < n; i++) observe(p[i]); }
+  u64 get() { if (!in.empty() || out.empty()) duplex(); u64 r = out.back(); out.pop_back(); return r; }
+  gl2 get_ext() { u64 a = get(); u64 b = get(); return gl2_make(a, b); }
+};
+
+struct PhaseTimer {  // CUDA-event timings of the prover phases (names follow plonky2's `timed!` labels)
+  sbn_ctx* ctx; std::vector<std::pair<std::string, cudaEvent_t>> ev;
+  explicit PhaseTimer(sbn_ctx* c) : ctx(c) { mark("start"); }
+  void mark(const char* name) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); ev.push_back({name, e}); }
+  std::string json() {
+    cudaEventSynchronize(ev.back().second);
+    std::ostringstream os; os << "{";
+    for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); os << (i > 1 ? "," : "") << "\"" << ev[i].first << "\":" << ms; }
+    float tot = 0; cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+    os << ",\"total\":" << tot << "}";
+    for (auto& e : ev) cudaEventDestroy(e.second);
+    ev.clear();
+    return os.str();
+  }
+};
+
+struct sbn_trace {
+  sbn_ctx* ctx; AirDesc air; int logn; DevBuf<u64> cols; std::vector<u64> results;
+};
+struct sbn_proof {
+  std::vector<uint8_t> bytes; std::string timings;
+  std::vector<u64> dbg_z, dbg_q, dbg_ch;
+};
+
+// Commitment to a batch of polynomials (plonky2 `PolynomialBatch`, blinding = false).
+struct Commitment {
+  DevBuf<u64> coeffs, lde; DevMerkleTree tree; int ncols = 0;
+};
+static void commit_from_coeffs(sbn_ctx* ctx, Commitment& c, int ncols, int logn, int rate_bits, int cap_height) {
+  size_t N = size_t(1) << logn;
+  c.ncols = ncols;
+  c.lde = DevBuf<u64>(ctx, (size_t)ncols * (N << rate_bits));
+  lde_columns(ctx, c.coeffs, c.lde, ncols, logn, rate_bits);
+  merkle_commit_lde(ctx, c.lde, ncols, logn, rate_bits, cap_height, &c.tree);
+}
+static void commit_from_values(sbn_ctx* ctx, Commitment& c, const u64* values, int ncols, int logn, int rate_bits, int cap_height) {
+  size_t N = size_t(1) << logn;
+  c.coeffs = DevBuf<u64>(ctx, (size_t)ncols * N);
+  intt_columns(ctx, values, c.coeffs, ncols, logn);
+  commit_from_coeffs(ctx, c, ncols, logn, rate_bits, cap_height);
+}
+
+struct Writer {  // canonical proof wire format: LE u64 field elements, u32 length prefixes, u8 option tag
+  std::vector<uint8_t>& b;
+  explicit Writer(std::vector<uint8_t>& v) : b(v) {}
+  void u8(uint8_t x) { b.push_back(x); }
+  void u32_(uint32_t x) { for (int i = 0; i < 4; i++) b.push_back((uint8_t)(x >> (8 * i))); }
+  void f(u64 x) { for (int i = 0; i < 8; i++) b.push_back((uint8_t)(x >> (8 * i))); }
+  void fs(const u64* p, size_t n) { size_t o = b.size(); b.resize(o + 8 * n); memcpy(b.data() + o, p, 8 * n); }  // little-endian host
+  void hashes(const u64* p, size_t nh) { u32_((uint32_t)nh); fs(p, 4 * nh); }
+  void fvec(const u64* p, size_t n) { u32_((uint32_t)n); fs(p, n); }
+  void evec(const u64* p, size_t n) { u32_((uint32_t)n); fs(p, 2 * n); }
+};
+
+static std::vector<int> reduction_arity_bits(const sbn_config& c, int degree_bits) {  // FriReductionStrategy::ConstantArityBits
+  std::vector<int> r;
+  while (degree_bits > (int)c.fri_final_poly_bits && degree_bits + (int)c.rate_bits - (int)c.fri_arity_bits >= (int)c.cap_height) {
+    r.push_back(c.fri_arity_bits); degree_bits -= c.fri_arity_bits;
+  }
+  return r;
+}
+
+static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr, const u64* public_inputs, size_t npis, sbn_proof* proof) {
+  const AirDesc& air = tr->air;
+  const int logn = tr->logn, rate_bits = cfg.rate_bits, cap_height = cfg.cap_height, nch = cfg.num_challenges;
+  const size_t N = size_t(1) << logn, L = N << rate_bits;
+  SBN_REQUIRE(npis == air.num_public_inputs, "public input count mismatch");
+  SBN_REQUIRE(cfg.coset_shift == 0 || cfg.coset_shift == GL_MULT_GENERATOR, "unsupported coset shift");
+  SBN_REQUIRE(nch >= 1 && nch <= SBN_MAX_CHALLENGES, "unsupported num_challenges");
+  SBN_REQUIRE(logn + rate_bits <= 30 && rate_bits >= 1 && rate_bits <= 4, "unsupported trace size / rate");
+  SBN_REQUIRE(cap_height <= logn + rate_bits && cfg.pow_bits >= 1, "bad FRI configuration");
+  std::vector<int> arities = reduction_arity_bits(cfg, logn);
+  int total_arities = 0; for (int a : arities) total_arities += a;
+  SBN_REQUIRE(total_arities <= logn + rate_bits - cap_height, "FRI total reduction arity is too large.");
+  for (size_t i = 0; i < npis; i++) SBN_REQUIRE(public_inputs[i] < GL_P, "public input is not a canonical field element");
+  PhaseTimer tm(ctx);
+  Writer w(proof->bytes);
+
+  // ---- trace commitment ----
+  Commitment trace_c;
+  commit_from_values(ctx, trace_c, tr->cols, (int)air.num_columns, logn, rate_bits, cap_height);
+  tm.mark("compute trace commitment");
+  Challenger ch;
+  ch.observe_n(trace_c.tree.cap.data(), trace_c.tree.cap.size());
+  w.hashes(trace_c.tree.cap.data(), trace_c.tree.cap.size() / 4);
+
+  // ---- permutation argument ----
+  const int qdf = air.quotient_degree_factor();
+  PermInstances perm;
+  Commitment z_c;
+  bool uses_perm = !air.perm_pairs.empty();
+  std::vector<u64> perm_challenges;  // [chal][slot] (beta, gamma)
+  if (uses_perm) {
+    const int batch = qdf;  // Stark::permutation_batch_size
+    perm_challenges.resize((size_t)nch * batch * 2);
+    for (int i = 0; i < nch; i++) for (int j = 0; j < batch; j++) { perm_challenges[(i * batch + j) * 2] = ch.get(); perm_challenges[(i * batch + j) * 2 + 1] = ch.get(); }
+    // get_permutation_batches: cartesian(pairs, 0..num_challenges) chunked by batch; slot s of a chunk uses sets[chal].challenges[s]
+    perm.batch_size = batch;
+    size_t ninst = air.perm_pairs.size() * nch, nz = (ninst + batch - 1) / batch;
+    perm.lhs.assign(nz * batch, 0xFFFFFFFFu); perm.rhs.assign(nz * batch, 0xFFFFFFFFu); perm.gamma.assign(nz * batch, 0); perm.count.assign(nz, 0);
+    size_t e = 0;
+    for (auto& pr : air.perm_pairs) for (int chal = 0; chal < nch; chal++, e++) {
+      size_t z = e / batch; int slot = (int)(e % batch);
+      perm.lhs[z * batch + slot] = pr.first; perm.rhs[z * batch + slot] = pr.second;
+      perm.gamma[z * batch + slot] = perm_challenges[(chal * batch + slot) * 2 + 1];
+      perm.count[z]++;
+    }
+    DevBuf<u64> zvals(ctx, nz * N);
+    compute_z_polys(ctx, tr->cols, logn, perm, zvals);
+    tm.mark("compute permutation Z polys");
+    if (getenv("SBN_DEBUG_INTERMEDIATES")) {
+      proof->dbg_z.resize(nz * N);
+      CUDA_CHECK(cudaMemcpyAsync(proof->dbg_z.data(), zvals, nz * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    commit_from_values(ctx, z_c, zvals, (int)nz, logn, rate_bits, cap_height);
+    tm.mark("compute permutation Z commitments");
+    ch.observe_n(z_c.tree.cap.data(), z_c.tree.cap.size());
+    w.u8(1); w.hashes(z_c.tree.cap.data(), z_c.tree.cap.size() / 4);
+  } else {
+    w.u8(0);
+  }
+
+  // ---- quotient ----
+  u64 alphas[SBN_MAX_CHALLENGES] = {0, 0};
+  for (int i = 0; i < nch; i++) alphas[i] = ch.get();
+  DevBuf<u64> d_pis(ctx, npis ? npis : 1);
+  if (npis) CUDA_CHECK(cudaMemcpyAsync(d_pis, public_inputs, npis * 8, cudaMemcpyHostToDevice, ctx->stream));
+  Commitment q_c;
+  const int nq_polys = qdf * nch;
+  q_c.coeffs = DevBuf<u64>(ctx, (size_t)nq_polys * N);
+  compute_quotient_chunks(ctx, air, trace_c.lde, uses_perm ? z_c.lde.get() : nullptr, perm, d_pis, alphas, nch, logn, rate_bits, q_c.coeffs);
+  tm.mark("compute quotient polys");
+  if (getenv("SBN_DEBUG_INTERMEDIATES")) {
+    proof->dbg_q.resize((size_t)nq_polys * N);
+    CUDA_CHECK(cudaMemcpyAsync(proof->dbg_q.data(), q_c.coeffs, proof->dbg_q.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  commit_from_coeffs(ctx, q_c, nq_polys, logn, rate_bits, cap_height);
+  tm.mark("compute quotient commitment");
+  ch.observe_n(q_c.tree.cap.data(), q_c.tree.cap.size());
+  w.hashes(q_c.tree.cap.data(), q_c.tree.cap.size() / 4);
+
+  // ---- openings ----
+  gl2 zeta = ch.get_ext();
+  u64 g = gl_root_of_unity(logn);
+  if (gl2_eq(gl2_pow(zeta, (u64)N), gl2_make(1, 0))) throw SbnError(SBN_ERR_INTERNAL, "Opening point is in the subgroup.");
+  gl2 zeta_next = gl2_mul_base(zeta, g);
+  const int C = (int)air.num_columns, Z = uses_perm ? z_c.ncols : 0;
+  DevBuf<u64> d_open(ctx, (size_t)(C + Z + nq_polys) * 4);
+  eval_columns_at_two_points(ctx, trace_c.coeffs, C, logn, zeta, zeta_next, d_open);
+  if (Z) eval_columns_at_two_points(ctx, z_c.coeffs, Z, logn, zeta, zeta_next, d_open + (size_t)C * 4);
+  eval_columns_at_two_points(ctx, q_c.coeffs, nq_polys, logn, zeta, zeta_next, d_open + (size_t)(C + Z) * 4);
+  std::vector<u64> open((size_t)(C + Z + nq_polys) * 4);
+  CUDA_CHECK(cudaMemcpyAsync(open.data(), d_open, open.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  // StarkOpeningSet { local_values, next_values, permutation_zs, permutation_zs_next, quotient_polys }
+  auto pick = [&](int first, int count, int which) { std::vector<u64> v((size_t)count * 2); for (int i = 0; i < count; i++) { v[2 * i] = open[(size_t)(first + i) * 4 + 2 * which]; v[2 * i + 1] = open[(size_t)(first + i) * 4 + 2 * which + 1]; } return v; };
+  std::vector<u64> local_values = pick(0, C, 0), next_values = pick(0, C, 1), pzs = pick(C, Z, 0), pzs_next = pick(C, Z, 1), qp = pick(C + Z, nq_polys, 0);
+  w.evec(local_values.data(), C); w.evec(next_values.data(), C);
+  if (uses_perm) { w.evec(pzs.data(), Z); w.evec(pzs_next.data(), Z); }
+  w.evec(qp.data(), nq_polys);
+  // challenger.observe_openings(to_fri_openings): zeta batch = local | zs | quotient, zeta_next batch = next | zs_next
+  ch.observe_n(local_values.data(), local_values.size()); ch.observe_n(pzs.data(), pzs.size()); ch.observe_n(qp.data(), qp.size());
+  ch.observe_n(next_values.data(), next_values.size()); ch.observe_n(pzs_next.data(), pzs_next.size());
+  tm.mark("compute openings");
+
+  // ---- FRI ----
+  gl2 fri_alpha = ch.get_ext();
+  std::vector<OracleView> views; views.push_back({trace_c.coeffs, C}); if (Z) views.push_back({z_c.coeffs, Z}); views.push_back({q_c.coeffs, nq_polys});
+  const int logL = logn + rate_bits;
+  DevBuf<u64> fcoeffs(ctx, 2 * L), fvalues(ctx, 2 * L);
+  fri_final_poly(ctx, views, logn, rate_bits, fri_alpha, zeta, zeta_next, fcoeffs);
+  tm.mark("reduce batch of polynomials");
+  u64 shift = GL_MULT_GENERATOR;
+  ntt_batch(ctx, fcoeffs, L, fvalues, L, 2, logL, false, get_pow_table(ctx, shift, logL), nullptr);
+  tm.mark("perform final FFT");
+  std::vector<FriLayer> layers(arities.size());
+  std::vector<gl2> betas;
+  int cur_log = logL;
+  DevBuf<u64> cur_coeffs = std::move(fcoeffs), cur_values = std::move(fvalues);
+  w.u32_((uint32_t)arities.size());
+  for (size_t li = 0; li < arities.size(); li++) {
+    int ab = arities[li];
+    fri_commit_layer(ctx, cur_values, cur_log, ab, cap_height, &layers[li]);
+    ch.observe_n(layers[li].tree.cap.data(), layers[li].tree.cap.size());
+    w.hashes(layers[li].tree.cap.data(), layers[li].tree.cap.size() / 4);
+    gl2 beta = ch.get_ext(); betas.push_back(beta);
+    size_t n = size_t(1) << cur_log, m = n >> ab;
+    DevBuf<u64> folded(ctx, 2 * m), vals(ctx, 2 * m);
+    fri_fold_coeffs(ctx, cur_coeffs, n, ab, beta, folded);
+    shift = gl_pow(shift, (u64)1 << ab);
+    cur_log -= ab;
+    ntt_batch(ctx, folded, m, vals, m, 2, cur_log, false, get_pow_table(ctx, shift, cur_log), nullptr);
+    cur_coeffs = std::move(folded); cur_values = std::move(vals);
+  }
+  // final polynomial: truncate by the rate, observe
+  size_t nfinal = (size_t(1) << cur_log) >> rate_bits;
+  std::vector<u64> fa(nfinal), fb(nfinal), final_poly(2 * nfinal);
+  CUDA_CHECK(cudaMemcpyAsync(fa.data(), cur_coeffs, nfinal * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(fb.data(), cur_coeffs + (size_t(1) << cur_log), nfinal * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < nfinal; i++) { final_poly[2 * i] = fa[i]; final_poly[2 * i + 1] = fb[i]; }
+  ch.observe_n(final_poly.data(), final_poly.size());
+  tm.mark("fold codewords in the commitment phase");
+  // proof of work (canonical choice: smallest valid witness; upstream accepts any -- SURVEY.md U2)
+  u64 pst[12]; memcpy(pst, ch.st, sizeof pst);
+  for (size_t i = 0; i < ch.in.size(); i++) pst[i] = ch.in[i];
+  u64 pow_witness = fri_pow_search(ctx, pst, (int)ch.in.size(), cfg.pow_bits);
+  ch.observe(pow_witness);
+  u64 pow_response = ch.get();
+  if ((pow_response >> (64 - cfg.pow_bits)) != 0) throw SbnError(SBN_ERR_INTERNAL, "proof-of-work self-check failed");
+  tm.mark("find proof-of-work witness");
+  // queries
+  std::vector<u64> indices(cfg.num_query_rounds);
+  for (auto& x : indices) x = ch.get() % L;
+  std::vector<QueryOracle> qo; qo.push_back({trace_c.lde, C, &trace_c.tree}); if (Z) qo.push_back({z_c.lde, Z, &z_c.tree}); qo.push_back({q_c.lde, nq_polys, &q_c.tree});
+  std::vector<FriLayer*> lp; for (auto& l : layers) lp.push_back(&l);
+  size_t rw = fri_query_record_words(qo, lp);
+  std::vector<u64> rec(rw * indices.size());
+  fri_gather_queries(ctx, qo, logn, rate_bits, lp, indices, rec.data());
+  w.u32_((uint32_t)indices.size());
+  for (size_t q = 0; q < indices.size(); q++) {
+    const u64* r = rec.data() + q * rw;
+    w.u32_((uint32_t)qo.size());
+    for (auto& o : qo) { w.fvec(r, o.ncols); r += o.ncols; w.hashes(r, o.tree->proof_len()); r += (size_t)o.tree->proof_len() * 4; }
+    w.u32_((uint32_t)lp.size());
+    for (auto* l : lp) { size_t ne = size_t(1) << l->arity_bits; w.evec(r, ne); r += 2 * ne; w.hashes(r, l->tree.proof_len()); r += (size_t)l->tree.proof_len() * 4; }
+  }
+  w.evec(final_poly.data(), nfinal);
+  w.f(pow_witness);
+  w.fvec(public_inputs, npis);
+  tm.mark("query rounds");
+  proof->timings = tm.json();
+  // challenges for parity tests: alphas | zeta | fri_alpha | permutation sets
+  proof->dbg_ch.clear();
+  for (int i = 0; i < nch; i++) proof->dbg_ch.push_back(alphas[i]);
+  proof->dbg_ch.push_back(zeta.a); proof->dbg_ch.push_back(zeta.b); proof->dbg_ch.push_back(fri_alpha.a); proof->dbg_ch.push_back(fri_alpha.b);
+  for (u64 v : perm_challenges) proof->dbg_ch.push_back(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+#define API_BEGIN try {
+#define API_END(ctx)                                                                             \
+  } catch (const SbnError& e) { if (ctx) (ctx)->last_error = e.what(); else g_create_error = e.what(); return e.code; } \
+  catch (const std::exception& e) { if (ctx) (ctx)->last_error = e.what(); else g_create_error = e.what(); return -4; }   \
+  return 0;
+
+extern "C" {
+int sbn_ctx_create(int device, void* cuda_stream, sbn_ctx** out) {
+  sbn_ctx* ctx = nullptr;
+  API_BEGIN
+  SBN_REQUIRE(out, "null output pointer");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) throw SbnError(-2, std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  SBN_REQUIRE(device >= 0 && device < ndev, "bad device index");
+  CUDA_CHECK(cudaSetDevice(device));
+  sbn_ctx* c = new sbn_ctx();
+  c->device = device;
+  if (cuda_stream) c->stream = (cudaStream_t)cuda_stream; else { CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->owns_stream = true; }
+  cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  API_END(ctx)
+}
+void sbn_ctx_destroy(sbn_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->release_all();
+  for (auto& kv : ctx->pow_tables) cudaFree(kv.second);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+const char* sbn_last_error(const sbn_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+int sbn_ctx_synchronize(sbn_ctx* ctx) { API_BEGIN CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); API_END(ctx) }
+uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx) { return ctx->launches; }
+uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx) { return ctx->bytes_allocated; }
+
+int sbn_config_standard_fast(sbn_config* out) {
+  if (!out) return -1;
+  *out = sbn_config{100, 2, 1, 4, 16, 4, 5, 84, GL_MULT_GENERATOR};
+  return 0;
+}
+int sbn_air_info(int air, size_t num_io, size_t* num_columns, size_t* num_public_inputs, size_t* num_rows, size_t* io_size, size_t* result_words,
+                 size_t* num_permutation_pairs) {
+  sbn_ctx* ctx = nullptr;
+  API_BEGIN
+  AirDesc a = make_air(air, num_io);
+  if (num_columns) *num_columns = a.num_columns;
+  if (num_public_inputs) *num_public_inputs = a.num_public_inputs;
+  if (num_rows) *num_rows = a.num_rows;
+  if (io_size) *io_size = a.io_size;
+  if (result_words) *result_words = a.result_words;
+  if (num_permutation_pairs) *num_permutation_pairs = a.perm_pairs.size();
+  API_END(ctx)
+}
+
+int sbn_trace_generate(sbn_ctx* ctx, int air, const void* ios, size_t num_io, sbn_trace** out) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && ios && out, "null argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  std::unique_ptr<sbn_trace> t(new sbn_trace());
+  t->ctx = ctx; t->air = make_air(air, num_io); t->logn = ilog2(t->air.num_rows);
+  t->cols = DevBuf<u64>(ctx, t->air.num_columns * t->air.num_rows);
+  t->results.resize(t->air.result_words * num_io);
+  generate_trace(ctx, t->air, ios, t->cols, t->results.data());
+  *out = t.release();
+  API_END(ctx)
+}
+int sbn_trace_upload(sbn_ctx* ctx, int air, size_t num_io, const uint64_t* cols, size_t ncols, size_t nrows, sbn_trace** out) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && cols && out, "null argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  std::unique_ptr<sbn_trace> t(new sbn_trace());
+  t->ctx = ctx; t->air = make_air(air, num_io);
+  SBN_REQUIRE(ncols == t->air.num_columns && nrows == t->air.num_rows, "trace shape does not match the AIR");
+  t->logn = ilog2(nrows);
+  t->cols = DevBuf<u64>(ctx, ncols * nrows);
+  CUDA_CHECK(cudaMemcpyAsync(t->cols, cols, ncols * nrows * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *out = t.release();
+  API_END(ctx)
+}
+int sbn_trace_download(const sbn_trace* t, uint64_t* cols_out) {
+  sbn_ctx* ctx = t ? t->ctx : nullptr;
+  API_BEGIN
+  SBN_REQUIRE(t && cols_out, "null argument");
+  CUDA_CHECK(cudaMemcpyAsync(cols_out, t->cols, t->air.num_columns * t->air.num_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+int sbn_trace_results(const sbn_trace* t, uint64_t* out) {
+  if (!t || !out) return -1;
+  memcpy(out, t->results.data(), t->results.size() * 8);
+  return 0;
+}
+void sbn_trace_free(sbn_trace* t) { delete t; }
+
+int sbn_public_inputs(int air, const void* ios, size_t num_io, uint64_t* out, size_t out_len) {
+  sbn_ctx* ctx = nullptr;
+  API_BEGIN
+  AirDesc a = make_air(air, num_io);
+  SBN_REQUIRE(out_len == a.num_public_inputs, "public input buffer has the wrong length");
+  format_public_inputs(a, ios, (u64*)out);
+  API_END(ctx)
+}
+
+int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs, sbn_proof** out) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && config && trace && out && (public_inputs || num_public_inputs == 0), "null argument");
+  SBN_REQUIRE(trace->ctx == ctx, "trace belongs to another context");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  std::unique_ptr<sbn_proof> p(new sbn_proof());
+  prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, p.get());
+  *out = p.release();
+  API_END(ctx)
+}
+int sbn_proof_serialize(const sbn_proof* proof, uint8_t* buf, size_t* len) {
+  if (!proof || !len) return -1;
+  if (!buf) { *len = proof->bytes.size(); return 0; }
+  if (*len < proof->bytes.size()) { *len = proof->bytes.size(); return -1; }
+  memcpy(buf, proof->bytes.data(), proof->bytes.size());
+  *len = proof->bytes.size();
+  return 0;
+}
+int sbn_proof_timings(const sbn_proof* proof, char* buf, size_t cap) {
+  if (!proof || !buf || cap == 0) return -1;
+  snprintf(buf, cap, "%s", proof->timings.c_str());
+  return 0;
+}
+int sbn_proof_debug(const sbn_proof* proof, int which, uint64_t* out, size_t cap_words, size_t* written) {
+  if (!proof || !written) return -1;
+  const std::vector<u64>* v = which == 0 ? &proof->dbg_z : which == 1 ? &proof->dbg_q : which == 2 ? &proof->dbg_ch : nullptr;
+  if (!v) return -1;
+  *written = v->size();
+  if (out) { if (cap_words < v->size()) return -1; memcpy(out, v->data(), v->size() * 8); }
+  return 0;
+}
+void sbn_proof_free(sbn_proof* p) { delete p; }
+
+__global__ void k_poseidon_batch(u64* states, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 st[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) st[k] = states[i * 12 + k];
+  poseidon_permute(st);
+#pragma unroll
+  for (int k = 0; k < 12; k++) states[i * 12 + k] = st[k];
+}
+int sbn_poseidon_permute(sbn_ctx* ctx, uint64_t* states, size_t n) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && states, "null argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  DevBuf<u64> d(ctx, n * 12);
+  CUDA_CHECK(cudaMemcpyAsync(d, states, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  k_poseidon_batch<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d, n);
+  LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaMemcpyAsync(states, d, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+__global__ void k_lde_to_natural(const u64* lde, u64* out, int logn, int rate_bits, size_t ncols) {
+  size_t L = size_t(1) << (logn + rate_bits), N = size_t(1) << logn;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= L * ncols) return;
+  size_t c = t / L, i = t % L;
+  out[t] = lde[c * L + (i & ((size_t(1) << rate_bits) - 1)) * N + (i >> rate_bits)];
+}
+int sbn_commit_columns(sbn_ctx* ctx, const uint64_t* values, size_t ncols, int logn, int rate_bits, int cap_height, uint64_t* coeffs_out,
+                       uint64_t* lde_out, uint64_t* cap_out) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && values && ncols > 0, "null argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t N = size_t(1) << logn, L = N << rate_bits;
+  DevBuf<u64> d_vals(ctx, ncols * N);
+  CUDA_CHECK(cudaMemcpyAsync(d_vals, values, ncols * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+  Commitment c;
+  commit_from_values(ctx, c, d_vals, (int)ncols, logn, rate_bits, cap_height);
+  if (coeffs_out) CUDA_CHECK(cudaMemcpyAsync(coeffs_out, c.coeffs, ncols * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lde_out) {
+    DevBuf<u64> nat(ctx, ncols * L);
+    k_lde_to_natural<<<(unsigned)((ncols * L + 255) / 256), 256, 0, ctx->stream>>>(c.lde, nat, logn, rate_bits, ncols);
+    LAUNCH_CHECK(ctx);
+    CUDA_CHECK(cudaMemcpyAsync(lde_out, nat, ncols * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (cap_out) memcpy(cap_out, c.tree.cap.data(), c.tree.cap.size() * 8);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+__global__ void k_fill_pseudo(u64* p, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 z = (i + 1) * 0x9E3779B97F4A7C15ULL; z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 32;
+  p[i] = z >= GL_P ? z - GL_P : z;
+}
+int sbn_bench_commit(sbn_ctx* ctx, size_t ncols, int logn, int rate_bits, int cap_height, int iters, float* ms) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && ms && iters > 0, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t N = size_t(1) << logn, L = N << rate_bits;
+  DevBuf<u64> vals(ctx, ncols * N), coeffs(ctx, ncols * N), lde(ctx, ncols * L);
+  k_fill_pseudo<<<(unsigned)((ncols * N + 255) / 256), 256, 0, ctx->stream>>>(vals, ncols * N);
+  LAUNCH_CHECK(ctx);
+  cudaEvent_t e[4]; for (auto& x : e) CUDA_CHECK(cudaEventCreate(&x));
+  ms[0] = ms[1] = ms[2] = 0;
+  for (int it = -1; it < iters; it++) {  // one warm-up
+    DevMerkleTree tree;
+    merkle_alloc(ctx, &tree, L, cap_height);
+    CUDA_CHECK(cudaEventRecord(e[0], ctx->stream));
+    intt_columns(ctx, vals, coeffs, (int)ncols, logn);
+    lde_columns(ctx, coeffs, lde, (int)ncols, logn, rate_bits);
+    CUDA_CHECK(cudaEventRecord(e[1], ctx->stream));
+    merkle_leaf_hash_only(ctx, lde, (int)ncols, logn, rate_bits, &tree);
+    CUDA_CHECK(cudaEventRecord(e[2], ctx->stream));
+    merkle_build_from_leaf_digests(ctx, &tree);
+    CUDA_CHECK(cudaEventRecord(e[3], ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(e[3]));
+    if (it >= 0) for (int k = 0; k < 3; k++) { float t; CUDA_CHECK(cudaEventElapsedTime(&t, e[k], e[k + 1])); ms[k] += t / iters; }
+  }
+  for (auto& x : e) cudaEventDestroy(x);
+  API_END(ctx)
+}
+}  // extern "C"

@@ -1,0 +1,174 @@
+// K5: quotient evaluation.  Replaces starky's `compute_quotient_polys` (external dependency;
+// SURVEY.md App. B.7) including the call-back into the reference's `eval_packed_generic`
+// (e.g. reference src/curves/g1/exp.rs:331-495) and `eval_permutation_checks`.
+//
+// One thread per point of the size-2N quotient coset; LDE columns are column-major so a warp reads
+// 32 consecutive values of each column it touches (the "next" row is the same run shifted by one).
+#include "quotient.cuh"
+#include "ntt.cuh"
+
+HD void qpoint_begin(const QArgs& a, size_t idx, QPoint& q) {
+  const size_t N = size_t(1) << a.logn;
+  const int bq = (int)(idx >> a.logn);
+  const size_t k = idx & (N - 1), kn = (k + 1) & (N - 1);
+  q.lp = a.trace + a.coset_off[bq] + k;
+  q.np = a.trace + a.coset_off[bq] + kn;
+  q.stride = a.trace_stride;
+  q.pi = a.pi;
+  F x(gl_mul(a.coset_shift[bq], a.wpow[k]));
+  q.z_last = x - F(a.w_inv);
+  q.l_first = F(a.lagrange[a.coset_off[bq] + k]);
+  q.l_last = F(a.lagrange[a.lagrange_stride + a.coset_off[bq] + k]);
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) { q.alpha[c] = F(a.alpha[c]); q.acc[c] = F(); }
+}
+HD void qpoint_end(const QArgs& a, size_t idx, const QPoint& q) {
+  const size_t N2 = size_t(2) << a.logn;
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) {
+    u64* p = a.acc + (size_t)c * N2 + idx;
+    F prev = a.first ? F() : F(*p) * F(a.alpha_m[c]);
+    *p = (prev + q.acc[c]).v;
+  }
+}
+
+// starky `eval_permutation_checks`: first-row Z-1 for every Z, then one product
+// constraint per Z.  2*nz constraints.
+HD void eval_permutation_checks(const QArgs& a, size_t idx, QPoint& q) {
+  const size_t N = size_t(1) << a.logn;
+  const int bq = (int)(idx >> a.logn);
+  const size_t k = idx & (N - 1), kn = (k + 1) & (N - 1);
+  const u64* zl = a.zs + a.coset_off[bq] + k;
+  const u64* zn = a.zs + a.coset_off[bq] + kn;
+  for (int i = 0; i < a.nz; i++) q.first_row(F(zl[(size_t)i * a.zs_stride]) - F(1));
+  for (int i = 0; i < a.nz; i++) {
+    F lhs(1), rhs(1);
+    for (int j = 0; j < a.perm_batch; j++) {
+      int e = i * a.perm_batch + j;
+      u32 l = a.perm_lhs[e];
+      if (l == 0xFFFFFFFFu) break;
+      F g(a.perm_gamma[e]);
+      lhs = lhs * (q.lv(l) + g);
+      rhs = rhs * (q.lv(a.perm_rhs[e]) + g);
+    }
+    q.constraint(F(zn[(size_t)i * a.zs_stride]) * rhs - F(zl[(size_t)i * a.zs_stride]) * lhs);
+  }
+}
+
+HD void eval_segment(const QArgs& a, const Segment& s, size_t idx, QPoint& q) {
+  switch (s.kind) {
+    case SEG_SPLIT_RANGE_CHECK: eval_split_u16_range_check(q, s.p0, s.p1, s.p2); break;
+    case SEG_MODULAR_CORE: eval_modular_stark_core(q); break;
+    case SEG_G1_CORE: eval_g1_exp_core(q, s.p0); break;
+    case SEG_FLAGS: eval_flags(q, s.p0); break;
+    case SEG_G1_ADD: eval_g1_add(q, q.lv(s.p1), s.p0); break;
+    case SEG_G1_DOUBLE: eval_g1_double(q, q.lv(s.p1), s.p0); break;
+    case SEG_PERIODIC_PULSE: eval_periodic_pulse(q, s.p0, s.p1, s.p2, s.p3); break;
+    case SEG_PULSE: eval_pulse(q, s.p0, s.p1, s.p2); break;
+    case SEG_U16_RANGE_CHECK: eval_u16_range_check(q, s.p0, s.p1); break;
+    case SEG_PERMUTATION: eval_permutation_checks(a, idx, q); break;
+  }
+}
+
+template <int KIND> __global__ void __launch_bounds__(128) k_segment(QArgs a, Segment s) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t(2) << a.logn)) return;
+  QPoint q;
+  qpoint_begin(a, idx, q);
+  Segment ss = s; ss.kind = (SegKind)KIND;   // compile-time kind: each instantiation keeps only its own code
+  eval_segment(a, ss, idx, q);
+  qpoint_end(a, idx, q);
+}
+
+static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
+  unsigned blocks = (unsigned)(((size_t(2) << a.logn) + 127) / 128);
+#define SEGCASE(K) case K: k_segment<K><<<blocks, 128, 0, ctx->stream>>>(a, s); break;
+  switch (s.kind) {
+    SEGCASE(SEG_SPLIT_RANGE_CHECK) SEGCASE(SEG_MODULAR_CORE) SEGCASE(SEG_G1_CORE) SEGCASE(SEG_FLAGS) SEGCASE(SEG_G1_ADD)
+    SEGCASE(SEG_G1_DOUBLE) SEGCASE(SEG_PERIODIC_PULSE) SEGCASE(SEG_PULSE) SEGCASE(SEG_U16_RANGE_CHECK) SEGCASE(SEG_PERMUTATION)
+  }
+#undef SEGCASE
+  LAUNCH_CHECK(ctx);
+}
+
+__global__ void k_fill_lagrange_coeffs(u64* coeffs, const u64* wpow, u64 ninv, size_t N) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  coeffs[j] = ninv;                      // ifft(selector(0))      = 1/N
+  coeffs[N + j] = gl_mul(ninv, wpow[j]);  // ifft(selector(N - 1))  = w^j / N
+}
+__global__ void k_scale_cosets(u64* acc, int logn, int num_challenges, u64 zh0, u64 zh1) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t N2 = size_t(2) << logn;
+  if (i >= N2 * num_challenges) return;
+  int bq = (int)((i % N2) >> logn);
+  acc[i] = gl_mul(acc[i], bq ? zh1 : zh0);
+}
+// f_lo = (u0 + u1)/2, f_hi = (u0 - u1)/(2 g^N): the two degree-N chunks of a degree-2N quotient
+// from its unscaled per-coset interpolants u_b = f_lo + (-1)^b g^N f_hi.
+__global__ void k_quotient_split(const u64* u0, const u64* u1, u64* lo, u64* hi, u64 inv2, u64 inv2gn, size_t N) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  u64 a = u0[j], b = u1[j];
+  lo[j] = gl_mul(gl_add(a, b), inv2);
+  hi[j] = gl_mul(gl_sub(a, b), inv2gn);
+}
+
+void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_lde, const u64* zs_lde, const PermInstances& perm,
+                             const u64* d_public_inputs, const u64* alphas, int num_challenges, int logn, int rate_bits, u64* out_chunks) {
+  SBN_REQUIRE(air.quotient_degree_factor() == 2, "only constraint_degree 3 (quotient degree factor 2) is supported");
+  SBN_REQUIRE(rate_bits >= 1, "constraint degree higher than the rate is not supported");
+  SBN_REQUIRE(num_challenges >= 1 && num_challenges <= SBN_MAX_CHALLENGES, "unsupported num_challenges");
+  const size_t N = size_t(1) << logn, R = size_t(1) << rate_bits, L = N * R;
+  const size_t step = size_t(1) << (rate_bits - 1);
+  const NttTables& tb = get_ntt_tables(ctx, logn);
+  // Lagrange selectors on the LDE cosets
+  DevBuf<u64> lag_coeffs(ctx, 2 * N), lag_lde(ctx, 2 * L);
+  u64 ninv = gl_inv((u64)N);
+  k_fill_lagrange_coeffs<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(lag_coeffs, tb.w_fwd, ninv, N);
+  LAUNCH_CHECK(ctx);
+  lde_columns(ctx, lag_coeffs, lag_lde, 2, logn, rate_bits);
+
+  DevBuf<u64> acc(ctx, (size_t)SBN_MAX_CHALLENGES * 2 * N);
+  QArgs a; memset(&a, 0, sizeof a);
+  a.trace = trace_lde; a.trace_stride = L; a.zs = zs_lde; a.zs_stride = L; a.logn = logn;
+  u64 w2n = gl_root_of_unity(logn + 1);
+  for (int bq = 0; bq < 2; bq++) { a.coset_off[bq] = (size_t)bq * step * N; a.coset_shift[bq] = gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, bq)); }
+  a.wpow = tb.w_fwd; a.w_inv = gl_inv(gl_root_of_unity(logn));
+  a.lagrange = lag_lde; a.lagrange_stride = L; a.pi = d_public_inputs; a.acc = acc;
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) a.alpha[c] = c < num_challenges ? alphas[c] : 0;
+  DevBuf<u32> d_lhs, d_rhs; DevBuf<u64> d_gamma;
+  std::vector<Segment> segs = air.segments;
+  if (perm.nz()) {
+    size_t ne = perm.lhs.size();
+    d_lhs = DevBuf<u32>(ctx, ne); d_rhs = DevBuf<u32>(ctx, ne); d_gamma = DevBuf<u64>(ctx, ne);
+    CUDA_CHECK(cudaMemcpyAsync(d_lhs, perm.lhs.data(), ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_rhs, perm.rhs.data(), ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_gamma, perm.gamma.data(), ne * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // host vectors may die before the copy runs otherwise
+    a.perm_lhs = d_lhs; a.perm_rhs = d_rhs; a.perm_gamma = d_gamma; a.perm_batch = perm.batch_size; a.nz = (int)perm.nz();
+    segs.push_back({SEG_PERMUTATION, 0, 0, 0, 0, 2 * perm.nz()});
+  }
+  bool first = true;
+  for (const Segment& s : segs) {
+    a.first = first ? 1 : 0;
+    for (int c = 0; c < SBN_MAX_CHALLENGES; c++) a.alpha_m[c] = gl_pow(a.alpha[c], s.num_constraints);
+    launch_segment(ctx, a, s);
+    first = false;
+  }
+  // divide by Z_H(x) = x^N - 1 = g^N (-1)^bq - 1
+  u64 gn = gl_exp_pow2(GL_MULT_GENERATOR, logn);
+  u64 zh0 = gl_inv(gl_sub(gn, 1)), zh1 = gl_inv(gl_sub(gl_neg(gn), 1));
+  size_t tot = 2 * N * num_challenges;
+  k_scale_cosets<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(acc, logn, num_challenges, zh0, zh1);
+  LAUNCH_CHECK(ctx);
+  // per-coset interpolation (coset_ifft restricted to each half), then split into the two chunks
+  DevBuf<u64> u(ctx, 2 * N);
+  u64 inv2 = gl_inv(2), inv2gn = gl_inv(gl_mul(2, gn));
+  for (int c = 0; c < num_challenges; c++) {
+    for (int bq = 0; bq < 2; bq++) {
+      const u64* post = get_pow_table(ctx, gl_inv(a.coset_shift[bq]), logn);
+      ntt_batch(ctx, acc + ((size_t)c * 2 + bq) * N, N, u + (size_t)bq * N, N, 1, logn, true, nullptr, post);
+    }
+    k_quotient_split<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(u, u + N, out_chunks + (size_t)(2 * c) * N, out_chunks + (size_t)(2 * c + 1) * N, inv2, inv2gn, N);
+    LAUNCH_CHECK(ctx);
+  }
+}

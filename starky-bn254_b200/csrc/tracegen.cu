@@ -1,0 +1,307 @@
+// K1: batched trace generation on the device.  Replaces the reference's serial, BigInt-based
+// `generate_trace` (reference src/curves/g1/exp.rs:255-318, src/modular/modular.rs:379-434) with:
+//   chain kernel  (one thread per instance, Jacobian double-and-add, no inversions)
+//   affine kernel (one thread per chain point)
+//   row kernel    (one thread per trace row: slope, limb products, quotient and carry witnesses)
+//   pulse / lookup kernels (closed forms, counting sort, and the reference's greedy table permutation).
+// The trace is written column-major, so the threads of a warp (32 consecutive rows) store 256
+// contiguous bytes per column.
+#include "tracegen.cuh"
+#include "witness.cuh"
+#include "../../include/starky_bn254_b200.h"
+
+struct ColWriter {
+  u64* base; size_t stride;
+  __device__ __forceinline__ void operator()(int col, u64 v) const { base[(size_t)col * stride] = v; }
+};
+
+// ---------------- lookups (reference src/utils/range_check.rs, src/utils/lookup.rs:60-111) ----------------
+struct LookupDesc { int src_col, shift, sorted_col, perm_col; };
+
+__global__ void k_table_col(u64* col, size_t N, u32 R) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r < N) col[r] = r < R ? r : R - 1;
+}
+__global__ void k_split_cols(const u64* src, u64* lo, u64* hi, size_t N) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r < N) { u64 v = src[r]; lo[r] = v & 0xFF; hi[r] = (v >> 8) & 0xFF; }
+}
+// histogram of (col >> shift) & (R-1); grid.y = lookup
+__global__ void __launch_bounds__(256) k_lookup_hist(const u64* __restrict__ cols, size_t N, u32 R, const LookupDesc* __restrict__ descs, u32* __restrict__ cnt,
+                                                     int* __restrict__ err) {
+  const LookupDesc d = descs[blockIdx.y];
+  const u64* src = cols + (size_t)d.src_col * N;
+  u32* c = cnt + (size_t)blockIdx.y * R;
+  __shared__ u32 sh[256];
+  const bool small = R <= 256;
+  if (small) { sh[threadIdx.x] = 0; __syncthreads(); }
+  for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < N; r += (size_t)gridDim.x * blockDim.x) {
+    u64 v = src[r] >> d.shift;
+    if (d.shift == 0 && v >= R) { *err = 1; v = R - 1; }   // reference asserts every target value < range_max
+    v &= (R - 1);
+    if (small) atomicAdd(&sh[v], 1u); else atomicAdd(&c[v], 1u);
+  }
+  if (small) { __syncthreads(); if (threadIdx.x < R && sh[threadIdx.x]) atomicAdd(&c[threadIdx.x], sh[threadIdx.x]); }
+}
+// One warp per lookup: counting-sort output and the greedy permuted table of `permuted_cols`
+// (lookup.rs:60-111) in histogram form: walking the table values v in order, a value absent from the inputs
+// is pushed on the unused stack; the first input copy of v takes the table's v, each further copy pops the
+// most recent unused value or, if none, is deferred; deferred positions finally take the leftover unused
+// values bottom-first.  The table's last value R-1 occurs N-R+1 times (range_check.rs:33-35).
+__global__ void __launch_bounds__(32) k_lookup_walk(const u32* __restrict__ cnt_all, u32 R, size_t N, u64* __restrict__ cols, const LookupDesc* __restrict__ descs,
+                                                    u32* __restrict__ stack_all, u32* __restrict__ defer_all) {
+  const int lane = threadIdx.x;
+  const LookupDesc d = descs[blockIdx.x];
+  const u32* cnt = cnt_all + (size_t)blockIdx.x * R;
+  u32* stack = stack_all + (size_t)blockIdx.x * R;
+  u32* defer = defer_all + (size_t)blockIdx.x * N;
+  u64* sorted = cols + (size_t)d.sorted_col * N;
+  u64* perm = cols + (size_t)d.perm_col * N;
+  size_t off = 0, ndef = 0; u32 top = 0;
+  for (u32 v0 = 0; v0 < R; v0 += 32) {
+    const u32 cl = cnt[v0 + lane];
+    for (int k = 0; k < 32; k++) {
+      const u32 v = v0 + k;
+      if (v == R - 1) break;
+      const u32 c = __shfl_sync(0xffffffffu, cl, k);
+      if (c == 0) {
+        if (lane == 0) stack[top] = v;
+        top++;
+      } else {
+        for (u32 t = lane; t < c; t += 32) sorted[off + t] = v;
+        if (lane == 0) perm[off] = v;
+        const u32 dd = c - 1, npop = dd < top ? dd : top;
+        for (u32 t = lane; t < npop; t += 32) perm[off + 1 + t] = stack[top - 1 - t];
+        top -= npop;
+        const u32 nd = dd - npop;
+        for (u32 t = lane; t < nd; t += 32) defer[ndef + t] = (u32)(off + 1 + npop + t);
+        ndef += nd; off += c;
+      }
+      __syncwarp();
+    }
+  }
+  {  // v = R-1: table holds tcount copies
+    const size_t c = cnt[R - 1], tcount = N - R + 1, m = c < tcount ? c : tcount;
+    for (size_t t = lane; t < c; t += 32) sorted[off + t] = R - 1;
+    for (size_t t = lane; t < m; t += 32) perm[off + t] = R - 1;
+    if (c > tcount) { for (size_t t = lane; t < c - tcount; t += 32) defer[ndef + t] = (u32)(off + tcount + t); ndef += c - tcount; }
+  }
+  __syncwarp();
+  for (size_t k = lane; k < ndef; k += 32) perm[defer[k]] = k < top ? stack[k] : R - 1;
+}
+
+static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::vector<LookupDesc>& descs) {
+  SBN_REQUIRE(N >= R, "range-check table does not fit the trace (reference asserts rows >= range_max)");
+  SBN_REQUIRE(N < (size_t(1) << 32), "trace too long");
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  // lookups are processed in groups so the scratch (stack + deferred list per lookup) stays bounded
+  size_t per = (N + R) * 4 + (size_t)R * 4;
+  size_t group = std::max<size_t>(1, (size_t(512) << 20) / per);
+  group = std::min(group, descs.size());
+  DevBuf<LookupDesc> d_desc(ctx, descs.size());
+  CUDA_CHECK(cudaMemcpyAsync(d_desc, descs.data(), descs.size() * sizeof(LookupDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  DevBuf<u32> cnt(ctx, group * R), stack(ctx, group * R), defer(ctx, group * N);
+  for (size_t g0 = 0; g0 < descs.size(); g0 += group) {
+    size_t ng = std::min(group, descs.size() - g0);
+    CUDA_CHECK(cudaMemsetAsync(cnt, 0, ng * R * 4, ctx->stream));
+    unsigned bx = (unsigned)std::min<size_t>((N + 255) / 256, 64);
+    k_lookup_hist<<<dim3(bx, (unsigned)ng), 256, 0, ctx->stream>>>(d_cols, N, R, d_desc + g0, cnt, err);
+    LAUNCH_CHECK(ctx);
+    k_lookup_walk<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer);
+    LAUNCH_CHECK(ctx);
+  }
+  int h_err = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  SBN_REQUIRE(!h_err, "range-checked column holds a value >= 2^16");
+}
+
+// reference src/utils/range_check.rs:20-47: table | (sorted_i, permuted_table_i) per target column
+void generate_u16_range_check_cols(sbn_ctx* ctx, u64* d_cols, size_t N, int t0, int ntargets, int start_lookups) {
+  k_table_col<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)start_lookups * N, N, 1u << 16);
+  LAUNCH_CHECK(ctx);
+  std::vector<LookupDesc> descs;
+  for (int i = 0; i < ntargets; i++) descs.push_back({t0 + i, 0, start_lookups + 1 + 2 * i, start_lookups + 2 + 2 * i});
+  run_lookups(ctx, d_cols, N, 1u << 16, descs);
+}
+// reference src/utils/range_check.rs:116-160: table | (lo, sorted_lo, perm_lo, hi, sorted_hi, perm_hi) per target
+void generate_split_u16_range_check_cols(sbn_ctx* ctx, u64* d_cols, size_t N, int t0, int ntargets, int main_col) {
+  k_table_col<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)main_col * N, N, 1u << 8);
+  LAUNCH_CHECK(ctx);
+  std::vector<LookupDesc> descs;
+  for (int i = 0; i < ntargets; i++) {
+    int b = main_col + 1 + 6 * i;
+    k_split_cols<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)(t0 + i) * N, d_cols + (size_t)b * N, d_cols + (size_t)(b + 3) * N, N);
+    LAUNCH_CHECK(ctx);
+    descs.push_back({b, 0, b + 1, b + 2});
+    descs.push_back({b + 3, 0, b + 4, b + 5});
+  }
+  run_lookups(ctx, d_cols, N, 1u << 8, descs);
+}
+
+// ---------------- ModularStark ----------------
+__global__ void __launch_bounds__(128) k_modular_rows(const u64* __restrict__ ios, u64* __restrict__ cols, size_t N) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  ColWriter w{cols + r, N};
+  modular_stark_row(ios + r * 8, w);
+}
+
+// ---------------- G1ExpStark ----------------
+struct G1Io { u64 x_x[4], x_y[4], off_x[4], off_y[4]; u32 exp[8]; u64 out_x[4], out_y[4]; };
+
+// chain points: A[k] = 2^k * x, B[k] = offset + sum_{j<k, bit_j} A[j], k = 0..256 (Jacobian, Montgomery)
+__global__ void __launch_bounds__(32) k_g1_chain(const G1Io* __restrict__ ios, size_t num_io, G1Jac* __restrict__ jac /* [io][2][257] */) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= num_io) return;
+  const G1Io& io = ios[i];
+  u32 w[8];
+  G1Jac A, B;
+  u64x4_to_words(io.x_x, w); A.x = fq_from_words(w); u64x4_to_words(io.x_y, w); A.y = fq_from_words(w); A.z = fq_one();
+  u64x4_to_words(io.off_x, w); B.x = fq_from_words(w); u64x4_to_words(io.off_y, w); B.y = fq_from_words(w); B.z = fq_one();
+  G1Jac* ja = jac + i * 2 * 257; G1Jac* jb = ja + 257;
+  ja[0] = A; jb[0] = B;
+  for (int k = 0; k < 256; k++) {
+    if ((io.exp[k >> 5] >> (k & 31)) & 1) B = g1_jac_add(A, B);
+    A = g1_jac_dbl(A);
+    ja[k + 1] = A; jb[k + 1] = B;
+  }
+}
+// Jacobian -> affine canonical words, one thread per chain point
+__global__ void __launch_bounds__(128) k_g1_affine(const G1Jac* __restrict__ jac, size_t npoints, u32* __restrict__ aff /* [point][16] */, int* __restrict__ err) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npoints) return;
+  G1Jac p = jac[i];
+  if (fq_is_zero(p.z)) { *err = 1; return; }
+  Fq zi = fq_inv(p.z), zi2 = fq_sqr(zi);
+  Fq x = fq_mul(p.x, zi2), y = fq_mul(p.y, fq_mul(zi2, zi));
+  u32 w[8];
+  fq_to_words(x, w);
+#pragma unroll
+  for (int k = 0; k < 8; k++) aff[i * 16 + k] = w[k];
+  fq_to_words(y, w);
+#pragma unroll
+  for (int k = 0; k < 8; k++) aff[i * 16 + 8 + k] = w[k];
+}
+// main columns: a(32) b(32) G1Output(320) flags(14)   (reference src/curves/g1/exp.rs:165-230, flags.rs:46-134)
+__global__ void __launch_bounds__(128) k_g1_rows(const G1Io* __restrict__ ios, const u32* __restrict__ aff, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const size_t inst = r >> 9; const int rr = (int)(r & 511), k = rr >> 1;
+  u32 e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = ios[inst].exp[i];
+  u64 fl[14];
+  flags_row(e, rr, fl);
+  const u32* pa = aff + ((inst * 2) * 257 + k) * 16;
+  const u32* pb = aff + ((inst * 2 + 1) * 257 + k + (rr & 1)) * 16;
+  u32 ax[8], ay[8], bx[8], by[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { ax[i] = pa[i]; ay[i] = pa[8 + i]; bx[i] = pb[i]; by[i] = pb[8 + i]; }
+  const int op = fl[2] ? G1_OP_DOUBLE : (fl[4] ? G1_OP_ADD : G1_OP_NONE);   // a = is_double, filtered_bit = is_add
+  ColWriter w{cols + r, N};
+  if (!g1_row(ax, ay, bx, by, op, w)) *err = 1;
+#pragma unroll
+  for (int i = 0; i < 14; i++) w(384 + i, fl[i]);
+}
+struct Inv64 { u64 v[64]; };
+// periodic pulse witness (reference src/utils/pulse.rs:100-144, period 64, first pulse 62): counter, inverse witness
+__global__ void k_periodic_pulse(u64* counter_col, u64* witness_col, size_t N, Inv64 inv) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  u32 c = (u32)((r + 1) & 63);
+  counter_col[r] = c; witness_col[r] = inv.v[c];
+}
+__global__ void k_inverse_table(u64* t, size_t N) {  // t[d] = d^-1, d in [1, N)
+  size_t d = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (d >= N) return;
+  t[d] = d ? gl_inv((u64)d) : 0;
+}
+// io pulses (reference src/utils/pulse.rs:20-43): counter | (witness_i, pulse_i) for positions 512k, 512k+511
+__global__ void __launch_bounds__(256) k_io_pulses(u64* __restrict__ cols /* at start_io_pulses */, size_t N, int rows_per_io, const u64* __restrict__ invtab) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  int i = blockIdx.y;  // position index
+  if (i == 0) cols[r] = r;
+  size_t pos = (size_t)(i >> 1) * rows_per_io + ((i & 1) ? rows_per_io - 1 : 0);
+  u64 wv = 0;
+  if (r > pos) wv = invtab[r - pos]; else if (r < pos) wv = gl_neg(invtab[pos - r]);
+  cols[(size_t)(1 + 2 * i) * N + r] = wv;
+  cols[(size_t)(2 + 2 * i) * N + r] = (r == pos) ? 1 : 0;
+}
+
+static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* d_cols, u64* h_results) {
+  const size_t n = air.num_io, N = air.num_rows;
+  static_assert(sizeof(G1Io) == sizeof(sbn_g1_exp_io), "io layout");
+  const sbn_g1_exp_io* h = (const sbn_g1_exp_io*)ios;
+  for (size_t i = 0; i < n; i++) {  // coordinates must be canonical residues
+    const uint64_t* c[4] = {h[i].x_x, h[i].x_y, h[i].offset_x, h[i].offset_y};
+    for (auto p : c) { u32 w[8]; u64x4_to_words((const u64*)p, w); SBN_REQUIRE(!fq_geq_p(w), "G1 coordinate is not a canonical Fq residue"); }
+  }
+  DevBuf<G1Io> d_ios(ctx, n);
+  CUDA_CHECK(cudaMemcpyAsync(d_ios, ios, n * sizeof(G1Io), cudaMemcpyHostToDevice, ctx->stream));
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  const size_t npoints = n * 2 * 257;
+  DevBuf<G1Jac> jac(ctx, npoints);
+  DevBuf<u32> aff(ctx, npoints * 16);
+  k_g1_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, jac); LAUNCH_CHECK(ctx);
+  k_g1_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx);
+  k_g1_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx);
+  // results: b on the last row of each block = B[256]
+  std::vector<u32> res(n * 16);
+  for (size_t i = 0; i < n; i++)
+    CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 16, aff + ((i * 2 + 1) * 257 + 256) * 16, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  const int sf = 384, pp = sf + 14, iop = pp + 2, lookups = iop + 1 + 4 * (int)n;
+  Inv64 inv;
+  for (int c = 0; c < 64; c++) inv.v[c] = c == 63 ? 0 : gl_inv(gl_sub((u64)c, 63));
+  k_periodic_pulse<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)pp * N, d_cols + (size_t)(pp + 1) * N, N, inv); LAUNCH_CHECK(ctx);
+  DevBuf<u64> invtab(ctx, N);
+  k_inverse_table<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(invtab, N); LAUNCH_CHECK(ctx);
+  k_io_pulses<<<dim3((unsigned)((N + 255) / 256), (unsigned)(2 * n)), 256, 0, ctx->stream>>>(d_cols + (size_t)iop * N, N, 512, invtab); LAUNCH_CHECK(ctx);
+  generate_u16_range_check_cols(ctx, d_cols, N, 0, 24 * 16 - 3, lookups);
+  int h_err = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  SBN_REQUIRE(!h_err, "degenerate G1 input: the chain hit the point at infinity or two points with equal x (the reference panics here)");
+  if (h_results) for (size_t i = 0; i < n; i++) memcpy(h_results + i * 8, res.data() + i * 16, 64);
+}
+
+static void generate_modular(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* d_cols) {
+  const size_t N = air.num_rows;
+  const u64* h = (const u64*)ios;
+  for (size_t i = 0; i < 2 * N; i++) { u32 w[8]; u64x4_to_words(h + 4 * i, w); SBN_REQUIRE(!fq_geq_p(w), "ModularStark input is not a canonical Fq residue"); }
+  DevBuf<u64> d_ios(ctx, N * 8);
+  CUDA_CHECK(cudaMemcpyAsync(d_ios, ios, N * 64, cudaMemcpyHostToDevice, ctx->stream));
+  k_modular_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, d_cols, N); LAUNCH_CHECK(ctx);
+  generate_split_u16_range_check_cols(ctx, d_cols, N, 32, 111, 145);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void generate_trace(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* d_cols, u64* h_results) {
+  switch (air.air_id) {
+    case SBN_AIR_MODULAR: generate_modular(ctx, air, ios, d_cols); break;
+    case SBN_AIR_G1_EXP: generate_g1(ctx, air, ios, d_cols, h_results); break;
+    default: throw SbnError(-3, "trace generation for this AIR is not implemented yet");
+  }
+}
+
+void format_public_inputs(const AirDesc& air, const void* ios, u64* out) {
+  switch (air.air_id) {
+    case SBN_AIR_MODULAR: break;
+    case SBN_AIR_G1_EXP: {  // reference src/curves/g1/exp.rs:124-135: x.x x.y offset.x offset.y exp_val output.x output.y, 8 u32 limbs each
+      const sbn_g1_exp_io* h = (const sbn_g1_exp_io*)ios;
+      for (size_t i = 0; i < air.num_io; i++) {
+        u64* o = out + 56 * i;
+        auto put = [&](const uint64_t* v, int slot) { for (int k = 0; k < 8; k++) o[8 * slot + k] = (v[k >> 1] >> (32 * (k & 1))) & 0xFFFFFFFFULL; };
+        put(h[i].x_x, 0); put(h[i].x_y, 1); put(h[i].offset_x, 2); put(h[i].offset_y, 3);
+        for (int k = 0; k < 8; k++) o[32 + k] = h[i].exp_val[k];
+        put(h[i].output_x, 5); put(h[i].output_y, 6);
+      }
+      break;
+    }
+    default: throw SbnError(-3, "public inputs for this AIR are not implemented yet");
+  }
+}
