@@ -60,6 +60,10 @@ const char* sbn_last_error(const sbn_ctx* ctx); /* ctx may be NULL: last error o
 int sbn_ctx_synchronize(sbn_ctx* ctx);
 uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx);  /* kernels launched so far through this context */
 uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx);  /* bytes held by the context's caching allocator */
+/* Optional CUDA-event timing of the kernel families on the context's stream.  enable != 0 starts (and
+ * resets) the collection; sbn_ctx_kernel_stats writes {"family":{"ms":total,"count":launch groups},...}. */
+int sbn_ctx_kernel_timing(sbn_ctx* ctx, int enable);
+int sbn_ctx_kernel_stats(sbn_ctx* ctx, char* buf, size_t cap);
 
 /* StarkConfig::standard_fast_config (every call site, e.g. src/curves/g1/exp.rs:250-253) */
 int sbn_config_standard_fast(sbn_config* out);
@@ -70,6 +74,8 @@ int sbn_air_info(int air, size_t num_io, size_t* num_columns, size_t* num_public
 /* K1: `stark.generate_trace(&inputs)` (src/curves/g1/exp.rs:290-318) on the GPU; `ios` is a host array of
  * num_io input records of the AIR's type. */
 int sbn_trace_generate(sbn_ctx* ctx, int air, const void* ios, size_t num_io, sbn_trace** out);
+/* Same with the input records already resident in device memory (`d_ios` is a device pointer). */
+int sbn_trace_generate_device(sbn_ctx* ctx, int air, const void* d_ios, size_t num_io, sbn_trace** out);
 /* Host-generated trace path: `cols` is column-major (ncols x nrows), the layout `prove` takes. */
 int sbn_trace_upload(sbn_ctx* ctx, int air, size_t num_io, const uint64_t* cols, size_t ncols, size_t nrows, sbn_trace** out);
 int sbn_trace_download(const sbn_trace* trace, uint64_t* cols_out);

@@ -6,6 +6,7 @@
 #include "stark.hpp"
 #include "air_modular.hpp"
 #include "air_g1.hpp"
+#include "sample.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -181,6 +182,18 @@ int orc_eval_constraints(void* p, const u64* lv, const u64* nv, const u64* pis, 
   for (size_t i = 0; i < nalpha; i++) out[i] = yc.accs[i].v;
   if (count) *count = yc.count;
   return 0;
+}
+// Bounded-sample timing (see sample.hpp): out_ms = {tracegen, commit, zpoly, quotient, openings, reduce, fri_tail}, each measured on
+// 1/2^shift of its work (FRI tail in full); the caller scales the sampled phases by 2^shift.
+int orc_time_sample(void* p, const void* ios, size_t num_io, const OrcConfig* c, int shift, double* out_ms) {
+  AirHandle* h = (AirHandle*)p;
+  try {
+    size_t nrows = orc_air_num_rows(p);
+    SampleTimes t = time_prove_sample(*h->air, nrows, to_cfg(c), shift);
+    if (h->id == AIR_G1_EXP && ios) t.tracegen_ms = time_g1_tracegen_sample(*static_cast<G1ExpStark*>(h->air.get()), g1_ios(ios, num_io), shift);
+    out_ms[0] = t.tracegen_ms; out_ms[1] = t.commit_ms; out_ms[2] = t.zpoly_ms; out_ms[3] = t.quotient_ms; out_ms[4] = t.openings_ms; out_ms[5] = t.reduce_ms; out_ms[6] = t.fri_ms;
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -2; }
 }
 // ---- intermediates of the last orc_prove call (for stage-by-stage parity tests) ----
 size_t orc_dbg_num_z() { return g_dbg.z_polys.size(); }

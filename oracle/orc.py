@@ -227,3 +227,16 @@ def check_trace(air, trace, pis):
     L.orc_check_trace.restype = C.c_long
     bad = L.orc_check_trace(C.c_void_p(air.h), _p(trace), C.c_size_t(trace.shape[1]), _p(pis), C.c_size_t(len(pis)), fb, C.byref(nc))
     return bad, (fb[0], fb[1]), nc.value
+
+
+def time_sample(air, ios, shift=3, cfg=None):
+    """Bounded-sample CPU timing; returns dict of phase -> estimated FULL-proof milliseconds (sampled phases scaled by 2^shift)."""
+    cfg = cfg or Config.standard_fast_config()
+    out = (C.c_double * 7)()
+    buf = C.create_string_buffer(bytes(ios), len(ios)) if ios else None
+    rc = lib().orc_time_sample(C.c_void_p(air.h), buf, C.c_size_t(air.num_io), C.byref(cfg), C.c_int(shift), out)
+    if rc != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+    names = ["tracegen", "commit", "zpoly", "quotient", "openings", "reduce", "fri_tail"]
+    est = {k: v * ((1 << shift) if k != "fri_tail" else 1) for k, v in zip(names, list(out))}
+    return est

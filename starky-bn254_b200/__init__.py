@@ -63,9 +63,12 @@ def lib():
         L.sbn_ctx_launch_count.argtypes = [vp]
         L.sbn_ctx_device_bytes.restype = C.c_uint64
         L.sbn_ctx_device_bytes.argtypes = [vp]
+        L.sbn_ctx_kernel_timing.argtypes = [vp, C.c_int]
+        L.sbn_ctx_kernel_stats.argtypes = [vp, C.c_char_p, sz]
         L.sbn_config_standard_fast.argtypes = [vp]
         L.sbn_air_info.argtypes = [C.c_int, sz] + [C.POINTER(sz)] * 6
         L.sbn_trace_generate.argtypes = [vp, C.c_int, vp, sz, C.POINTER(vp)]
+        L.sbn_trace_generate_device.argtypes = [vp, C.c_int, vp, sz, C.POINTER(vp)]
         L.sbn_trace_upload.argtypes = [vp, C.c_int, sz, u64p, sz, sz, C.POINTER(vp)]
         L.sbn_trace_download.argtypes = [vp, u64p]
         L.sbn_trace_results.argtypes = [vp, u64p]
@@ -110,6 +113,14 @@ class Context:
     @property
     def device_bytes(self):
         return int(lib().sbn_ctx_device_bytes(self.h))
+
+    def kernel_timing(self, enable=True):
+        self.check(lib().sbn_ctx_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_stats(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.check(lib().sbn_ctx_kernel_stats(self.h, buf, 1 << 16))
+        return json.loads(buf.value.decode() or "{}")
 
     def close(self):
         if self.h:
@@ -231,6 +242,22 @@ class _Stark:
         h = C.c_void_p()
         buf = C.create_string_buffer(bytes(inputs), len(inputs))
         c.check(lib().sbn_trace_generate(c.h, self.AIR, buf, self.num_io, C.byref(h)))
+        return Trace(c, h, self)
+
+    def generate_trace_ptr(self, host_ptr, nbytes, ctx=None):
+        """K1 from a raw host pointer (e.g. a pinned torch tensor's data_ptr()); no extra host copy."""
+        c = self._ctx(ctx)
+        if nbytes != self.io_size * self.num_io:
+            raise ValueError("inputs has the wrong length")
+        h = C.c_void_p()
+        c.check(lib().sbn_trace_generate(c.h, self.AIR, C.c_void_p(host_ptr), self.num_io, C.byref(h)))
+        return Trace(c, h, self)
+
+    def generate_trace_device(self, device_ptr, ctx=None):
+        """K1 with the input records already resident in HBM (device pointer)."""
+        c = self._ctx(ctx)
+        h = C.c_void_p()
+        c.check(lib().sbn_trace_generate_device(c.h, self.AIR, C.c_void_p(device_ptr), self.num_io, C.byref(h)))
         return Trace(c, h, self)
 
     def upload_trace(self, cols, ctx=None):

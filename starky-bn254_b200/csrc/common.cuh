@@ -41,6 +41,23 @@ struct sbn_ctx {
   std::map<int, NttTables> ntt_tables;
   std::map<std::pair<u64, int>, u64*> pow_tables;  // (base, logn) -> base^i, i < 2^logn
   unsigned long long launches = 0;                 // kernels launched by this library (bench: gpu_launches)
+  // optional per-kernel-family CUDA-event timing on ctx->stream (bench.py roofline + breakdown)
+  bool ktime_enabled = false;
+  struct KPending { std::string name; cudaEvent_t a, b; };
+  std::vector<KPending> kpending;
+  std::vector<cudaEvent_t> kpool;
+  struct KStat { double ms = 0; unsigned long long count = 0; };
+  std::map<std::string, KStat> kstats;
+  cudaEvent_t kevent() { if (!kpool.empty()) { cudaEvent_t e = kpool.back(); kpool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+  void kresolve() {
+    for (auto& p : kpending) {
+      cudaEventSynchronize(p.b);
+      float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
+      auto& st = kstats[p.name]; st.ms += ms; st.count++;
+      kpool.push_back(p.a); kpool.push_back(p.b);
+    }
+    kpending.clear();
+  }
 
   void* alloc(size_t bytes) {
     if (bytes == 0) bytes = 8;
@@ -84,6 +101,13 @@ template <class T> struct DevBuf {
   ~DevBuf() { reset(); }
   T* get() const { return p; }
   operator T*() const { return p; }
+};
+
+// Times everything enqueued on ctx->stream during its lifetime under `name` (no-op unless enabled).
+struct KScope {
+  sbn_ctx* ctx; cudaEvent_t a; const char* name;
+  KScope(sbn_ctx* c, const char* n) : ctx(c), a(nullptr), name(n) { if (c->ktime_enabled) { a = c->kevent(); cudaEventRecord(a, c->stream); } }
+  ~KScope() { if (a) { cudaEvent_t b = ctx->kevent(); cudaEventRecord(b, ctx->stream); ctx->kpending.push_back({name, a, b}); } }
 };
 
 #define LAUNCH_CHECK(ctx) do { (ctx)->launches++; CUDA_CHECK(cudaGetLastError()); } while (0)

@@ -46,6 +46,7 @@ static DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1)
 void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, gl2 zeta, gl2 zeta_next, u64* d_out) {
   if (ncols <= 0) return;
   DevBuf<u64> pw = two_point_power_table(ctx, logn, zeta, zeta_next);
+  KScope ks(ctx, "openings_eval");
   k_eval_two_points<<<ncols, 256, 0, ctx->stream>>>(coeffs, size_t(1) << logn, pw, d_out);
   LAUNCH_CHECK(ctx);
 }
@@ -119,6 +120,7 @@ void fri_final_poly(sbn_ctx* ctx, const std::vector<OracleView>& oracles, int lo
     int nc = oracles[o].ncols;
     int cpg = (nc + G - 1) / G, ng = (nc + cpg - 1) / cpg;
     dim3 grid((unsigned)((N + 255) / 256), ng);
+    KScope ks(ctx, "fri_reduce_columns");
     k_reduce_columns<<<grid, 256, 0, ctx->stream>>>(oracles[o].coeffs, N, nc, cpg, apow, apow + total, off, partial); LAUNCH_CHECK(ctx);
     bool last = o + 1 == oracles.size();
     if (last) CUDA_CHECK(cudaMemcpyAsync(comp0, comp1, 2 * N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -211,6 +213,7 @@ u64 fri_pow_search(sbn_ctx* ctx, const u64 state[12], int pos, int pow_bits) {
   CUDA_CHECK(cudaMemcpyAsync(best, &h, 8, cudaMemcpyHostToDevice, ctx->stream));
   const u64 batch = 1ULL << (pow_bits + 2 > 22 ? 22 : pow_bits + 2);
   for (u64 base = 0;; base += batch) {
+    KScope ks(ctx, "fri_pow");
     k_pow<<<(unsigned)(batch / 128), 128, 0, ctx->stream>>>(st, pos, pow_bits, base, best);
     LAUNCH_CHECK(ctx);
     CUDA_CHECK(cudaMemcpyAsync(&h, best, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -286,6 +289,7 @@ void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, i
   size_t rw = fri_query_record_words(oracles, layers), nq = indices.size();
   DevBuf<u64> d_idx(ctx, nq), d_out(ctx, nq * rw);
   CUDA_CHECK(cudaMemcpyAsync(d_idx, indices.data(), nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+  KScope ks(ctx, "fri_gather_queries");
   k_gather_queries<<<(unsigned)nq, 256, 0, ctx->stream>>>(d, d_idx, rw, d_out);
   LAUNCH_CHECK(ctx);
   CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, nq * rw * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -70,6 +70,7 @@ void merkle_alloc(sbn_ctx* ctx, DevMerkleTree* t, size_t nleaves, int cap_height
 
 void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t) {
   size_t n = t->nleaves;
+  KScope ks(ctx, "merkle_tree_levels");
   for (int l = 0; l + 1 < t->num_levels(); l++) {
     size_t np = n >> 1;
     k_merkle_level<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(t->digests + t->level_off[l], t->digests + t->level_off[l + 1], np);
@@ -83,6 +84,7 @@ void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t) {
 
 void merkle_leaf_hash_only(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int rate_bits, DevMerkleTree* t) {
   size_t L = size_t(1) << (logn + rate_bits);
+  KScope ks(ctx, "merkle_leaf_hash");
   k_leaf_hash<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(lde, L, ncols, logn, rate_bits, t->digests);
   LAUNCH_CHECK(ctx);
 }

@@ -166,6 +166,7 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
   if (logn <= 11) {
     size_t smem = (N + N / 2) * 8;
     int threads = N >= 512 ? 256 : (N >= 64 ? (int)(N / 2) : 32);
+    KScope ks(ctx, "ntt_small");
     k_ntt_small<<<ncols, threads, smem, ctx->stream>>>(in, in_stride, out, out_stride, W, prescale, postscale, scale, logn);
     LAUNCH_CHECK(ctx);
     return;
@@ -191,8 +192,10 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
   for (size_t c0 = 0; c0 < (size_t)ncols; c0 += chunk) {
     unsigned nc = (unsigned)std::min(chunk, (size_t)ncols - c0);
     dim3 g1((unsigned)(1u << (l2 - logT1)), nc), g2((unsigned)(1u << (l1 - logT2)), nc);
+    { KScope ks(ctx, "ntt_pass1");
     k_ntt_pass1<<<g1, 512, smem1, ctx->stream>>>(in + c0 * in_stride, in_stride, tmp, W, prescale, l1, l2, logT1);
-    LAUNCH_CHECK(ctx);
+    LAUNCH_CHECK(ctx); }
+    KScope ks2(ctx, "ntt_pass2");
     k_ntt_pass2<<<g2, 512, smem2, ctx->stream>>>(tmp, out + c0 * out_stride, out_stride, W, postscale, scale, l1, l2, logT2);
     LAUNCH_CHECK(ctx);
   }

@@ -306,6 +306,8 @@ void sbn_ctx_destroy(sbn_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->release_all();
+  ctx->kresolve();
+  for (auto e : ctx->kpool) cudaEventDestroy(e);
   for (auto& kv : ctx->pow_tables) cudaFree(kv.second);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -315,6 +317,23 @@ int sbn_ctx_synchronize(sbn_ctx* ctx) { API_BEGIN CUDA_CHECK(cudaStreamSynchroni
 uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx) { return ctx->launches; }
 uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx) { return ctx->bytes_allocated; }
 
+int sbn_ctx_kernel_timing(sbn_ctx* ctx, int enable) {
+  if (!ctx) return -1;
+  ctx->kresolve();
+  ctx->ktime_enabled = enable != 0;
+  ctx->kstats.clear();
+  return 0;
+}
+int sbn_ctx_kernel_stats(sbn_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx || !buf || !cap) return -1;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->kresolve();
+  std::ostringstream os; os << "{"; bool first = true;
+  for (auto& kv : ctx->kstats) { os << (first ? "" : ",") << "\"" << kv.first << "\":{\"ms\":" << kv.second.ms << ",\"count\":" << kv.second.count << "}"; first = false; }
+  os << "}";
+  snprintf(buf, cap, "%s", os.str().c_str());
+  return 0;
+}
 int sbn_config_standard_fast(sbn_config* out) {
   if (!out) return -1;
   *out = sbn_config{100, 2, 1, 4, 16, 4, 5, 84, GL_MULT_GENERATOR};
@@ -334,7 +353,7 @@ int sbn_air_info(int air, size_t num_io, size_t* num_columns, size_t* num_public
   API_END(ctx)
 }
 
-int sbn_trace_generate(sbn_ctx* ctx, int air, const void* ios, size_t num_io, sbn_trace** out) {
+static int trace_generate_impl(sbn_ctx* ctx, int air, const void* ios, bool on_device, size_t num_io, sbn_trace** out) {
   API_BEGIN
   SBN_REQUIRE(ctx && ios && out, "null argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -342,10 +361,12 @@ int sbn_trace_generate(sbn_ctx* ctx, int air, const void* ios, size_t num_io, sb
   t->ctx = ctx; t->air = make_air(air, num_io); t->logn = ilog2(t->air.num_rows);
   t->cols = DevBuf<u64>(ctx, t->air.num_columns * t->air.num_rows);
   t->results.resize(t->air.result_words * num_io);
-  generate_trace(ctx, t->air, ios, t->cols, t->results.data());
+  generate_trace(ctx, t->air, ios, on_device, t->cols, t->results.data());
   *out = t.release();
   API_END(ctx)
 }
+int sbn_trace_generate(sbn_ctx* ctx, int air, const void* ios, size_t num_io, sbn_trace** out) { return trace_generate_impl(ctx, air, ios, false, num_io, out); }
+int sbn_trace_generate_device(sbn_ctx* ctx, int air, const void* d_ios, size_t num_io, sbn_trace** out) { return trace_generate_impl(ctx, air, d_ios, true, num_io, out); }
 int sbn_trace_upload(sbn_ctx* ctx, int air, size_t num_io, const uint64_t* cols, size_t ncols, size_t nrows, sbn_trace** out) {
   API_BEGIN
   SBN_REQUIRE(ctx && cols && out, "null argument");

@@ -78,7 +78,16 @@ template <int KIND> __global__ void __launch_bounds__(128) k_segment(QArgs a, Se
   qpoint_end(a, idx, q);
 }
 
+static const char* seg_name(SegKind k) {
+  switch (k) {
+    case SEG_SPLIT_RANGE_CHECK: return "q_split_range_check"; case SEG_MODULAR_CORE: return "q_modular_core"; case SEG_G1_CORE: return "q_g1_core";
+    case SEG_FLAGS: return "q_flags"; case SEG_G1_ADD: return "q_g1_add"; case SEG_G1_DOUBLE: return "q_g1_double"; case SEG_PERIODIC_PULSE: return "q_periodic_pulse";
+    case SEG_PULSE: return "q_pulse"; case SEG_U16_RANGE_CHECK: return "q_u16_range_check"; case SEG_PERMUTATION: return "q_permutation";
+  }
+  return "q_other";
+}
 static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
+  KScope ks(ctx, seg_name(s.kind));
   unsigned blocks = (unsigned)(((size_t(2) << a.logn) + 127) / 128);
 #define SEGCASE(K) case K: k_segment<K><<<blocks, 128, 0, ctx->stream>>>(a, s); break;
   switch (s.kind) {

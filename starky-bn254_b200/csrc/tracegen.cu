@@ -107,8 +107,10 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
     size_t ng = std::min(group, descs.size() - g0);
     CUDA_CHECK(cudaMemsetAsync(cnt, 0, ng * R * 4, ctx->stream));
     unsigned bx = (unsigned)std::min<size_t>((N + 255) / 256, 64);
+    { KScope ks(ctx, "lookup_hist");
     k_lookup_hist<<<dim3(bx, (unsigned)ng), 256, 0, ctx->stream>>>(d_cols, N, R, d_desc + g0, cnt, err);
-    LAUNCH_CHECK(ctx);
+    LAUNCH_CHECK(ctx); }
+    KScope ks2(ctx, "lookup_walk");
     k_lookup_walk<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer);
     LAUNCH_CHECK(ctx);
   }
@@ -142,9 +144,10 @@ void generate_split_u16_range_check_cols(sbn_ctx* ctx, u64* d_cols, size_t N, in
 }
 
 // ---------------- ModularStark ----------------
-__global__ void __launch_bounds__(128) k_modular_rows(const u64* __restrict__ ios, u64* __restrict__ cols, size_t N) {
+__global__ void __launch_bounds__(128) k_modular_rows(const u64* __restrict__ ios, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
+  { u32 c[8]; u64x4_to_words(ios + r * 8, c); if (fq_geq_p(c)) *err = 1; u64x4_to_words(ios + r * 8 + 4, c); if (fq_geq_p(c)) *err = 1; }
   ColWriter w{cols + r, N};
   modular_stark_row(ios + r * 8, w);
 }
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(128) k_modular_rows(const u64* __restrict__ io
 struct G1Io { u64 x_x[4], x_y[4], off_x[4], off_y[4]; u32 exp[8]; u64 out_x[4], out_y[4]; };
 
 // chain points: A[k] = 2^k * x, B[k] = offset + sum_{j<k, bit_j} A[j], k = 0..256 (Jacobian, Montgomery)
-__global__ void __launch_bounds__(32) k_g1_chain(const G1Io* __restrict__ ios, size_t num_io, G1Jac* __restrict__ jac /* [io][2][257] */) {
+__global__ void __launch_bounds__(32) k_g1_chain(const G1Io* __restrict__ ios, size_t num_io, G1Jac* __restrict__ jac /* [io][2][257] */, int* __restrict__ err) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= num_io) return;
   const G1Io& io = ios[i];
@@ -161,6 +164,10 @@ __global__ void __launch_bounds__(32) k_g1_chain(const G1Io* __restrict__ ios, s
   G1Jac A, B;
   u64x4_to_words(io.x_x, w); A.x = fq_from_words(w); u64x4_to_words(io.x_y, w); A.y = fq_from_words(w); A.z = fq_one();
   u64x4_to_words(io.off_x, w); B.x = fq_from_words(w); u64x4_to_words(io.off_y, w); B.y = fq_from_words(w); B.z = fq_one();
+  {  // coordinates must be canonical residues (arkworks cannot even represent others)
+    u32 c[8]; const u64* ps[4] = {io.x_x, io.x_y, io.off_x, io.off_y};
+    for (int t = 0; t < 4; t++) { u64x4_to_words(ps[t], c); if (fq_geq_p(c)) *err = 2; }
+  }
   G1Jac* ja = jac + i * 2 * 257; G1Jac* jb = ja + 257;
   ja[0] = A; jb[0] = B;
   for (int k = 0; k < 256; k++) {
@@ -232,24 +239,24 @@ __global__ void __launch_bounds__(256) k_io_pulses(u64* __restrict__ cols /* at 
   cols[(size_t)(2 + 2 * i) * N + r] = (r == pos) ? 1 : 0;
 }
 
-static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* d_cols, u64* h_results) {
+static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols, u64* h_results) {
   const size_t n = air.num_io, N = air.num_rows;
   static_assert(sizeof(G1Io) == sizeof(sbn_g1_exp_io), "io layout");
-  const sbn_g1_exp_io* h = (const sbn_g1_exp_io*)ios;
-  for (size_t i = 0; i < n; i++) {  // coordinates must be canonical residues
-    const uint64_t* c[4] = {h[i].x_x, h[i].x_y, h[i].offset_x, h[i].offset_y};
-    for (auto p : c) { u32 w[8]; u64x4_to_words((const u64*)p, w); SBN_REQUIRE(!fq_geq_p(w), "G1 coordinate is not a canonical Fq residue"); }
+  DevBuf<G1Io> d_ios_buf;
+  const G1Io* d_ios = (const G1Io*)ios;
+  if (!on_device) {
+    d_ios_buf = DevBuf<G1Io>(ctx, n);
+    CUDA_CHECK(cudaMemcpyAsync(d_ios_buf, ios, n * sizeof(G1Io), cudaMemcpyHostToDevice, ctx->stream));
+    d_ios = d_ios_buf;
   }
-  DevBuf<G1Io> d_ios(ctx, n);
-  CUDA_CHECK(cudaMemcpyAsync(d_ios, ios, n * sizeof(G1Io), cudaMemcpyHostToDevice, ctx->stream));
   DevBuf<int> err(ctx, 1);
   CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
   const size_t npoints = n * 2 * 257;
   DevBuf<G1Jac> jac(ctx, npoints);
   DevBuf<u32> aff(ctx, npoints * 16);
-  k_g1_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, jac); LAUNCH_CHECK(ctx);
-  k_g1_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx);
-  k_g1_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx);
+  { KScope ks(ctx, "g1_chain"); k_g1_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "g1_affine"); k_g1_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "g1_rows"); k_g1_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx); }
   // results: b on the last row of each block = B[256]
   std::vector<u32> res(n * 16);
   for (size_t i = 0; i < n; i++)
@@ -260,30 +267,39 @@ static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* 
   k_periodic_pulse<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)pp * N, d_cols + (size_t)(pp + 1) * N, N, inv); LAUNCH_CHECK(ctx);
   DevBuf<u64> invtab(ctx, N);
   k_inverse_table<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(invtab, N); LAUNCH_CHECK(ctx);
+  KScope ksp(ctx, "io_pulses");
   k_io_pulses<<<dim3((unsigned)((N + 255) / 256), (unsigned)(2 * n)), 256, 0, ctx->stream>>>(d_cols + (size_t)iop * N, N, 512, invtab); LAUNCH_CHECK(ctx);
   generate_u16_range_check_cols(ctx, d_cols, N, 0, 24 * 16 - 3, lookups);
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  SBN_REQUIRE(h_err != 2, "G1 coordinate is not a canonical Fq residue");
   SBN_REQUIRE(!h_err, "degenerate G1 input: the chain hit the point at infinity or two points with equal x (the reference panics here)");
   if (h_results) for (size_t i = 0; i < n; i++) memcpy(h_results + i * 8, res.data() + i * 16, 64);
 }
 
-static void generate_modular(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* d_cols) {
+static void generate_modular(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols) {
   const size_t N = air.num_rows;
-  const u64* h = (const u64*)ios;
-  for (size_t i = 0; i < 2 * N; i++) { u32 w[8]; u64x4_to_words(h + 4 * i, w); SBN_REQUIRE(!fq_geq_p(w), "ModularStark input is not a canonical Fq residue"); }
-  DevBuf<u64> d_ios(ctx, N * 8);
-  CUDA_CHECK(cudaMemcpyAsync(d_ios, ios, N * 64, cudaMemcpyHostToDevice, ctx->stream));
-  k_modular_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, d_cols, N); LAUNCH_CHECK(ctx);
+  DevBuf<u64> d_ios_buf; const u64* d_ios = (const u64*)ios;
+  if (!on_device) {
+    d_ios_buf = DevBuf<u64>(ctx, N * 8);
+    CUDA_CHECK(cudaMemcpyAsync(d_ios_buf, ios, N * 64, cudaMemcpyHostToDevice, ctx->stream));
+    d_ios = d_ios_buf;
+  }
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  { KScope ks(ctx, "modular_rows"); k_modular_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, d_cols, N, err); LAUNCH_CHECK(ctx); }
   generate_split_u16_range_check_cols(ctx, d_cols, N, 32, 111, 145);
+  int h_err = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  SBN_REQUIRE(!h_err, "ModularStark input is not a canonical Fq residue");
 }
 
-void generate_trace(sbn_ctx* ctx, const AirDesc& air, const void* ios, u64* d_cols, u64* h_results) {
+void generate_trace(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool ios_on_device, u64* d_cols, u64* h_results) {
   switch (air.air_id) {
-    case SBN_AIR_MODULAR: generate_modular(ctx, air, ios, d_cols); break;
-    case SBN_AIR_G1_EXP: generate_g1(ctx, air, ios, d_cols, h_results); break;
+    case SBN_AIR_MODULAR: generate_modular(ctx, air, ios, ios_on_device, d_cols); break;
+    case SBN_AIR_G1_EXP: generate_g1(ctx, air, ios, ios_on_device, d_cols, h_results); break;
     default: throw SbnError(-3, "trace generation for this AIR is not implemented yet");
   }
 }

@@ -102,6 +102,7 @@ void compute_z_polys(sbn_ctx* ctx, const u64* trace, int logn, const PermInstanc
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   DevBuf<u64> tn(ctx, (size_t)nz * ntiles), td(ctx, (size_t)nz * ntiles);
   dim3 grid(ntiles, nz);
+  KScope ks(ctx, "zpoly");
   k_z_tile_products<<<grid, ZT, 0, ctx->stream>>>(trace, N, d_lhs, d_rhs, d_gamma, perm.batch_size, tn, td, ntiles);
   LAUNCH_CHECK(ctx);
   k_z_tile_scan<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(tn, td, ntiles, nz);
