@@ -24,21 +24,15 @@ __global__ void __launch_bounds__(128) k_leaf_hash(const u64* __restrict__ lde, 
 #pragma unroll
     for (int c = 0; c < 4; c++) if (c < ncols) st[c] = p[(size_t)c * col_stride];
   } else {
-    int c = 0;
-    for (; c + 8 <= ncols; c += 8) {
+    // single loop / single inlined permutation (instruction-cache footprint); the ragged tail keeps the
+    // old state in the lanes it does not overwrite (overwrite-mode sponge, no padding)
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += 8) {
       u64 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) v[i] = p[(size_t)(c + i) * col_stride];
+      for (int i = 0; i < 8; i++) v[i] = (c + i < ncols) ? p[(size_t)(c + i) * col_stride] : st[i];
 #pragma unroll
       for (int i = 0; i < 8; i++) st[i] = v[i];
-      poseidon_permute(st);
-    }
-    if (c < ncols) {
-      u64 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) v[i] = (c + i < ncols) ? p[(size_t)(c + i) * col_stride] : 0;
-#pragma unroll
-      for (int i = 0; i < 8; i++) if (c + i < ncols) st[i] = v[i];
       poseidon_permute(st);
     }
   }

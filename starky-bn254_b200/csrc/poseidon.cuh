@@ -1,7 +1,15 @@
 // Poseidon-Goldilocks (width 12, rate 8, 4+22+4 rounds, x^7) -- the hash of plonky2's
 // PoseidonGoldilocksConfig, which the reference selects at every prove() call site
-// (e.g. reference src/curves/g1/exp.rs:788-790).  One permutation per thread, state in registers;
-// the MDS layer works on the 32-bit halves of each lane so every product is a 32x(6-bit) IMAD.
+// (e.g. reference src/curves/g1/exp.rs:788-790).  One permutation per thread, state in registers.
+//
+// Device path (the hot kernel of the whole prover: ~40 M permutations per G1 proof):
+//  * lanes are kept as arbitrary u64 representatives (NOT canonical) between operations; only the
+//    values leaving the permutation are canonicalised, so every result equals the canonical algorithm;
+//  * 64x64 multiply and the 2^64 = 2^32 - 1, 2^96 = -1 reduction are PTX carry chains (23 instructions);
+//  * the MDS layer works on the 32-bit halves of each lane (every product is a 32 x 9-bit IMAD), the next
+//    round's constants are added to the un-reduced accumulators, and one 10-instruction reduction per lane
+//    brings the < 2^75 sums back to 64 bits.
+// Host path (Fiat-Shamir challenger, a few dozen permutations per proof): plain canonical arithmetic.
 #pragma once
 #include "gl.cuh"
 
@@ -9,13 +17,120 @@ static const u64 h_poseidon_rc[360] = {
 #include "poseidon_rc.inc"
     SBN_POSEIDON_RC_LIST};
 #ifdef __CUDACC__
-static __constant__ u64 d_poseidon_rc[360] = {SBN_POSEIDON_RC_LIST};
+static __constant__ u64 d_poseidon_rc[372] = {SBN_POSEIDON_RC_LIST, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // + a zero "round 30"
 #endif
 
+#ifdef __CUDACC__
+// MDS coefficients as run-time constant-bank operands: with literal constants ptxas strength-reduces the
+// products into 64-bit shift/add chains, which more than doubles the instruction count of the MDS layer.
+static __constant__ u32 d_mds_c[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20, 8};
+#endif
 #ifdef __CUDA_ARCH__
 #define POSEIDON_RC(i) d_poseidon_rc[i]
 #else
 #define POSEIDON_RC(i) h_poseidon_rc[i]
+#endif
+
+#ifdef __CUDA_ARCH__
+// a * b mod p as an arbitrary 64-bit representative; a, b arbitrary u64.
+__device__ __forceinline__ u64 gl_mul_nc(u64 a, u64 b) {
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0, x1, x2, x3, m, c, bw;\n\t"
+      // 128-bit product x3:x2:x1:x0
+      "mul.lo.u32 x0, %2, %4;\n\t"
+      "mul.hi.u32 x1, %2, %4;\n\t"
+      "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
+      "madc.hi.u32 x2, %2, %5, 0;\n\t"
+      "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32 x3, 0, 0;\n\t"
+      "mad.lo.cc.u32 x2, %3, %5, x2;\n\t"
+      "madc.hi.u32 x3, %3, %5, x3;\n\t"
+      // t = (x1:x0) - x3            (2^96 = -1); a borrow wraps by 2^64 = EPS
+      "sub.cc.u32 x0, x0, x3;\n\t"
+      "subc.cc.u32 x1, x1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 x0, x0, m;\n\t"
+      "subc.u32 x1, x1, 0;\n\t"
+      // r = t + x2 * (2^32 - 1)     (2^64 = 2^32 - 1)
+      "add.cc.u32 x1, x1, x2;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 x0, x0, x2;\n\t"
+      "subc.cc.u32 x1, x1, 0;\n\t"
+      "subc.u32 bw, 0, 0;\n\t"
+      "add.u32 c, c, bw;\n\t"        // net wrap count: 0 or 1
+      "neg.s32 c, c;\n\t"            // 0 or 0xFFFFFFFF (= EPS)
+      "add.cc.u32 %0, x0, c;\n\t"
+      "addc.u32 %1, x1, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return ((u64)r1 << 32) | r0;
+}
+// a + b mod p, a arbitrary u64, b canonical (< p); result arbitrary u64 representative.
+__device__ __forceinline__ u64 gl_add_nc(u64 a, u64 b) {
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 c;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\t"
+      "addc.cc.u32 %1, %3, %5;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "neg.s32 c, c;\n\t"
+      "add.cc.u32 %0, %0, c;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+__device__ __forceinline__ u64 poseidon_sbox_nc(u64 x) {
+  u64 x2 = gl_mul_nc(x, x), x3 = gl_mul_nc(x2, x), x4 = gl_mul_nc(x2, x2);
+  return gl_mul_nc(x3, x4);
+}
+// s <- MDS * s + rc[rc_off ..] (the next round's constants; offset 360 = zeros), lanes arbitrary u64 in and out.
+__device__ __forceinline__ void poseidon_mds_nc(u64 s[12], int rc_off) {
+  u32 lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    const u64 rc = d_poseidon_rc[rc_off + k];
+    u64 al = (u32)rc, ah = rc >> 32;
+    // one IMAD.WIDE per term (left to itself the compiler strength-reduces the small constants into
+    // shift/add sequences on 64-bit pairs, which more than doubles the instruction count of this layer)
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + k) % 12]), "r"(d_mds_c[i]));
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + k) % 12]), "r"(d_mds_c[i]));
+    }
+    if (k == 0) {
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[0]), "r"(d_mds_c[12]));
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[0]), "r"(d_mds_c[12]));
+    }
+    // value = al + ah * 2^32, al, ah < 2^42.  128-bit form: lo64 = al + (ah0 << 32), hi = ah1 + carry (< 2^11);
+    // then lo64 + hi * (2^32 - 1) with one conditional wrap fix.
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 l1, h, t0, t1, c;\n\t"
+        "add.cc.u32 l1, %3, %4;\n\t"      // al1 + ah0
+        "addc.u32 h, %5, 0;\n\t"          // ah1 + carry
+        "sub.cc.u32 t0, 0, h;\n\t"        // (h << 32) - h
+        "subc.u32 t1, h, 0;\n\t"
+        "add.cc.u32 %0, %2, t0;\n\t"
+        "addc.cc.u32 %1, l1, t1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 c, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"((u32)al), "r"((u32)(al >> 32)), "r"((u32)ah), "r"((u32)(ah >> 32)));
+    s[k] = ((u64)r1 << 32) | r0;
+  }
+}
 #endif
 
 HD u64 poseidon_sbox(u64 x) {
@@ -45,22 +160,75 @@ HD void poseidon_mds(u64 s[12]) {
   }
 }
 
+// Canonical in, canonical out.
 HD void poseidon_permute(u64 s[12]) {
+#ifdef __CUDA_ARCH__
+  // One rolled round loop (uniform `full` branch) keeps the hot body ~24 KB so it stays in the
+  // instruction cache; a fully unrolled permutation (>90 KB) stalls on instruction fetch.
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl_add_nc(s[i], d_poseidon_rc[i]);
+#ifndef POSEIDON_LOOP_MODE
+#define POSEIDON_LOOP_MODE 0
+#endif
+#if POSEIDON_LOOP_MODE == 0
+#pragma unroll 1
+  for (int r = 0; r < 30; r++) {
+    s[0] = poseidon_sbox_nc(s[0]);
+    if (r < 4 || r >= 26) {
+#pragma unroll
+      for (int i = 1; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
+    }
+    poseidon_mds_nc(s, 12 * (r + 1));
+  }
+#elif POSEIDON_LOOP_MODE == 1
+  // full x4 | partial x22 | full x4 with one copy of each body
   int r = 0;
-  for (; r < 4; r++) {
+#pragma unroll 1
+  for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++, r++) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add(s[i], POSEIDON_RC(12 * r + i)));
-    poseidon_mds(s);
+      for (int i = 0; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
+      poseidon_mds_nc(s, 12 * (r + 1));
+    }
+    if (phase == 0) {
+#pragma unroll 1
+      for (int k = 0; k < 22; k++, r++) {
+        s[0] = poseidon_sbox_nc(s[0]);
+        poseidon_mds_nc(s, 12 * (r + 1));
+      }
+    }
   }
-  for (; r < 26; r++) {
+#elif POSEIDON_LOOP_MODE == 2
+  // partial rounds unrolled by two
+  int r = 0;
+#pragma unroll 1
+  for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++, r++) {
 #pragma unroll
+      for (int i = 0; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
+      poseidon_mds_nc(s, 12 * (r + 1));
+    }
+    if (phase == 0) {
+#pragma unroll 1
+      for (int k = 0; k < 11; k++, r += 2) {
+        s[0] = poseidon_sbox_nc(s[0]);
+        poseidon_mds_nc(s, 12 * (r + 1));
+        s[0] = poseidon_sbox_nc(s[0]);
+        poseidon_mds_nc(s, 12 * (r + 2));
+      }
+    }
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+#else
+  for (int r = 0; r < 30; r++) {
     for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_RC(12 * r + i));
-    s[0] = poseidon_sbox(s[0]);
+    if (r < 4 || r >= 26) { for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]); }
+    else s[0] = poseidon_sbox(s[0]);
     poseidon_mds(s);
   }
-  for (; r < 30; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add(s[i], POSEIDON_RC(12 * r + i)));
-    poseidon_mds(s);
-  }
+#endif
 }

@@ -267,8 +267,8 @@ static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   k_periodic_pulse<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)pp * N, d_cols + (size_t)(pp + 1) * N, N, inv); LAUNCH_CHECK(ctx);
   DevBuf<u64> invtab(ctx, N);
   k_inverse_table<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(invtab, N); LAUNCH_CHECK(ctx);
-  KScope ksp(ctx, "io_pulses");
-  k_io_pulses<<<dim3((unsigned)((N + 255) / 256), (unsigned)(2 * n)), 256, 0, ctx->stream>>>(d_cols + (size_t)iop * N, N, 512, invtab); LAUNCH_CHECK(ctx);
+  { KScope ksp(ctx, "io_pulses");
+    k_io_pulses<<<dim3((unsigned)((N + 255) / 256), (unsigned)(2 * n)), 256, 0, ctx->stream>>>(d_cols + (size_t)iop * N, N, 512, invtab); LAUNCH_CHECK(ctx); }
   generate_u16_range_check_cols(ctx, d_cols, N, 0, 24 * 16 - 3, lookups);
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));

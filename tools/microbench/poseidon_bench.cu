@@ -1,0 +1,55 @@
+// Micro-benchmark of the leaf-hash kernel variants (not product code): synthetic LDE, 2^17 leaves.
+#include "../../starky-bn254_b200/csrc/poseidon.cuh"
+#include <cstdio>
+#include <vector>
+
+template <int BS, int MINB> __global__ void __launch_bounds__(BS, MINB) k_leaf(const u64* __restrict__ lde, size_t L, int ncols, u64* __restrict__ digests) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = 0;
+  const u64* p = lde + idx;
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 8) {
+    u64 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = p[(size_t)(c + i) * L];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = v[i];
+    poseidon_permute(st);
+  }
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + idx * 4);
+  d[0] = make_ulonglong2(st[0], st[1]); d[1] = make_ulonglong2(st[2], st[3]);
+}
+__global__ void k_fill(u64* p, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 z = (i + 1) * 0x9E3779B97F4A7C15ULL; z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 32;
+  p[i] = z >= GL_P ? z - GL_P : z;
+}
+template <int BS, int MINB> float run(const u64* lde, size_t L, int ncols, u64* dig, int iters) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  k_leaf<BS, MINB><<<(unsigned)((L + BS - 1) / BS), BS>>>(lde, L, ncols, dig);
+  cudaEventRecord(a);
+  for (int i = 0; i < iters; i++) k_leaf<BS, MINB><<<(unsigned)((L + BS - 1) / BS), BS>>>(lde, L, ncols, dig);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  return ms / iters;
+}
+int main(int argc, char** argv) {
+  int logL = argc > 1 ? atoi(argv[1]) : 17, ncols = argc > 2 ? atoi(argv[2]) : 256;
+  size_t L = size_t(1) << logL;
+  u64 *lde, *dig;
+  cudaMalloc(&lde, L * ncols * 8); cudaMalloc(&dig, L * 32);
+  k_fill<<<(unsigned)((L * ncols + 255) / 256), 256>>>(lde, L * ncols);
+  std::vector<u64> h(4);
+  double perms = (double)L * (ncols / 8);
+  float ms;
+#define RUN(BS, MINB) ms = run<BS, MINB>(lde, L, ncols, dig, 3); cudaMemcpy(h.data(), dig + 4 * 777, 32, cudaMemcpyDeviceToHost); \
+  printf("%s bs=%d minb=%d  %.3f ms  %.1f Mperm/s  dig=%016llx\n", VARIANT, BS, MINB, ms, perms / ms / 1e3, h[0]);
+  RUN(128, 1) RUN(128, 8) RUN(128, 10) RUN(128, 12) RUN(64, 16) RUN(64, 20) RUN(256, 4) RUN(32, 32)
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
