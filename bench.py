@@ -21,9 +21,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-NUM_IO = 128
-WORKLOAD = "G1ExpStark num_io=128: 128 independent BN254 G1 scalar multiplications per proof, 2^16 rows x 1676 columns, StarkConfig::standard_fast_config"
 SAMPLE_SHIFT = 3
+# --air selects the AIR; the headline (BASELINE.json configs[1], default) is g1.  (class, oracle id, num_io, input generator, metric, workload)
+AIRS = {
+    "g1": ("G1ExpStark", 2, 128, "g1_exp_ios", "G1 scalar-mul STARK proofs/sec",
+           "G1ExpStark num_io=128: 128 independent BN254 G1 scalar multiplications per proof, 2^16 rows x 1676 columns, StarkConfig::standard_fast_config"),
+    "g2": ("G2ExpStark", 3, 128, "g2_exp_ios", "G2 scalar-mul STARK proofs/sec",
+           "G2ExpStark num_io=128: 128 independent BN254 G2 scalar multiplications per proof, 2^16 rows x 2822 columns, StarkConfig::standard_fast_config"),
+    "fq12": ("Fq12ExpStark", 4, 16, "fq12_exp_ios", "Fq12-exp STARK proofs/sec",
+             "Fq12ExpStark num_io=16: 16 independent BN254 Fq12 exponentiations (254-bit exponent) per proof, 2^13 rows x 9802 columns, StarkConfig::standard_fast_config"),
+    "fq": ("FqExpStark", 1, 128, "fq_exp_ios", "Fq-exp STARK proofs/sec",
+           "FqExpStark num_io=128: 128 independent BN254 Fq exponentiations per proof, 2^16 rows x 960 columns, StarkConfig::standard_fast_config"),
+}
+AIR = "g1"
+NUM_IO = 128
+WORKLOAD = AIRS["g1"][5]
+METRIC = AIRS["g1"][4]
+
+
+def select_air(name):
+    global AIR, NUM_IO, WORKLOAD, METRIC
+    AIR, NUM_IO, WORKLOAD, METRIC = name, AIRS[name][2], AIRS[name][5], AIRS[name][4]
 
 
 class ClockSampler(threading.Thread):
@@ -51,7 +69,7 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_sample(orc, ios):
-    air = orc.Air(orc.AIR_G1_EXP, NUM_IO)
+    air = orc.Air(AIRS[AIR][1], NUM_IO)
     t0 = time.perf_counter()
     est = orc.time_sample(air, ios, SAMPLE_SHIFT)
     wall = time.perf_counter() - t0
@@ -66,7 +84,7 @@ def run_reference(args):
         return
     orc = entry.load_oracle()
     sbn = entry.load_package()
-    ios = sbn.synthetic.g1_exp_ios(NUM_IO)
+    ios = getattr(sbn.synthetic, AIRS[AIR][3])(NUM_IO)
     cores = os.cpu_count()
     for _ in range(args.warmup):
         cpu_sample(orc, ios)
@@ -78,9 +96,9 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     ms = statistics.mean(fulls)
     value = 1000.0 / ms
-    sample = ("per step: every heavy phase of G1 trace generation + prove on 1/%d of its columns / instances / LDE points, scaled x%d; "
+    sample = ("per step: every heavy phase of trace generation + prove on 1/%d of its columns / instances / LDE points, scaled x%d; "
               "FRI tail in full (oracle/sample.hpp); est. phases ms=%s" % (1 << SAMPLE_SHIFT, 1 << SAMPLE_SHIFT, {k: round(v, 1) for k, v in est.items()}))
-    line = {"impl": "reference", "metric": "G1 scalar-mul STARK proofs/sec", "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks field)",
             "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample},
@@ -96,7 +114,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--air", default="g1", choices=sorted(AIRS))
     args = ap.parse_args()
+    select_air(args.air)
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -116,15 +136,18 @@ def main():
     sbn = entry.load_package()
     stream = torch.cuda.current_stream()
     ctx = sbn.Context(local, stream.cuda_stream)
-    stark = sbn.G1ExpStark(NUM_IO, ctx)
+    from starky_bn254_b200 import sharding
+    stark = getattr(sbn, AIRS[AIR][0])(NUM_IO, ctx)
     cfg = stark.config()
     syn = sbn.synthetic
+    gen_ios = getattr(syn, AIRS[AIR][3])
+    out_off = stark.io_size - 8 * stark.result_words
 
     # distinct synthetic batches per step and per rank; host copies pinned, device copies resident
     nb = args.steps + args.warmup
     host_ios = []
     for b in range(min(nb, 4)):   # 4 distinct batches, reused round-robin (input generation is host big-int work)
-        raw = syn.g1_exp_ios(NUM_IO, seed=0x5EED0001 + 1000 * rank + b)
+        raw = gen_ios(NUM_IO, seed=0x5EED0001 + 1000 * rank + b)
         t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
         host_ios.append(t)
     dev_ios = [t.cuda(non_blocking=True) for t in host_ios]
@@ -133,7 +156,7 @@ def main():
     def step_resident(i):
         tr = stark.generate_trace_device(dev_ios[i % len(dev_ios)].data_ptr())
         res = tr.results()
-        ios = syn.fill_g1_outputs(bytes(host_ios[i % len(host_ios)].numpy().tobytes()), res)
+        ios = syn.fill_outputs(bytes(host_ios[i % len(host_ios)].numpy().tobytes()), res, stark.io_size, out_off)
         pi = stark.generate_public_inputs(ios)
         p = sbn.prove(stark, cfg, tr, pi)
         tr.free()
@@ -143,7 +166,7 @@ def main():
         h = host_ios[i % len(host_ios)]
         tr = stark.generate_trace_ptr(h.data_ptr(), h.numel())
         res = tr.results()
-        ios = syn.fill_g1_outputs(bytes(h.numpy().tobytes()), res)
+        ios = syn.fill_outputs(bytes(h.numpy().tobytes()), res, stark.io_size, out_off)
         pi = stark.generate_public_inputs(ios)
         p = sbn.prove(stark, cfg, tr, pi)
         tr.free()
@@ -179,18 +202,19 @@ def main():
     barrier()
     t0 = time.perf_counter()
     nbytes = 0
+    last_proof_bytes = b""
     for i in range(args.steps):
-        nbytes = len(step_e2e(args.warmup + i))
+        last_proof_bytes = step_e2e(args.warmup + i)
+        nbytes = len(last_proof_bytes)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     sampler.stop_flag.set()
     sampler.join()
 
-    times = torch.tensor([ms_total, e2e_s * 1000.0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(times[0]), float(times[1])
+    ms_total, e2e_ms = sharding.max_over_ranks([ms_total, e2e_s * 1000.0], device="cuda")
+    # the only other cross-rank traffic: digests of the last proof of every rank (the "gather" of SURVEY §8e)
+    digests = sharding.gather_digests({rank: last_proof_bytes}, world, device="cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -211,14 +235,15 @@ def main():
     perms_per_proof = L * ((stark.num_columns + 7) // 8 + (nz + 7) // 8) + 3 * (L - 16)
     total_kernel_ms = sum(v["ms"] for v in kstats.values())
     line = {
-        "metric": "G1 scalar-mul STARK proofs/sec", "value": world * args.steps / (ms_total / 1e3), "unit": "proofs/s", "n_gpus": world,
+        "metric": METRIC, "value": world * args.steps / (ms_total / 1e3), "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (Goldilocks field; BN254 Fq on 8x32-bit limbs)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "instances_per_proof": NUM_IO, "parallelism": "independent proofs, 1 process per GPU, no collective",
                    "l2_policy": "per-proof working set ~5 GB >> 126 MB L2 (no flush needed)"},
         "instances_per_s": world * args.steps * NUM_IO / (ms_total / 1e3),
-        "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": NUM_IO * 224 + stark.num_public_inputs * 8,
-                "d2h_bytes_per_step": nbytes + NUM_IO * 64},
+        "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": NUM_IO * stark.io_size + stark.num_public_inputs * 8,
+                "d2h_bytes_per_step": nbytes + NUM_IO * stark.result_words * 8},
+        "proof_sha256_per_rank": [d[0][:16] for d in digests],
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon Merkle leaves)", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -232,7 +257,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         orc = entry.load_oracle()
-        full_ms, est, wall = cpu_sample(orc, syn.g1_exp_ios(NUM_IO))
+        full_ms, est, wall = cpu_sample(orc, gen_ios(NUM_IO))
         line["cpu_baseline"] = {"value": 1000.0 / full_ms, "unit": "proofs/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "oracle (C++/OpenMP restatement, not the Rust binary): heavy phases on 1/%d of their columns/instances/points scaled x%d, "
                                           "FRI tail in full; %.1f s of CPU wall; est. full-proof phases ms=%s" % (1 << SAMPLE_SHIFT, 1 << SAMPLE_SHIFT, wall, {k: round(v, 1) for k, v in est.items()})}

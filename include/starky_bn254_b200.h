@@ -50,6 +50,17 @@ typedef struct {
   uint32_t exp_val[8];
   uint64_t output_x[4], output_y[4];
 } sbn_g1_exp_io;
+/* Input record of FqExpStark, replaces `FqExpIONative` (src/fields/fq/exp.rs:88-93): output = offset * x^exp_val. */
+typedef struct { uint64_t x[4], offset[4]; uint32_t exp_val[8]; uint64_t output[4]; } sbn_fq_exp_io;
+/* Input record of G2ExpStark, replaces `G2ExpIONative` (src/curves/g2/exp.rs:90-95).  A point is x.c0, x.c1, y.c0, y.c1
+ * (four canonical 256-bit residues, the order of `g2_exp_io_to_columns`, src/curves/g2/exp.rs:139-156). */
+typedef struct { uint64_t x[16], offset[16]; uint32_t exp_val[8]; uint64_t output[16]; } sbn_g2_exp_io;
+/* Input record of Fq12ExpStark, replaces `Fq12ExpIONative` (src/fields/fq12/exp.rs:90-95).  An Fq12 element is its 12
+ * coefficients in the flat `MyFq12` order the reference converts to before writing columns (src/fields/fq12/exp.rs:107-124,
+ * src/utils/utils.rs:174-183): element = sum_{i<6} (c[i] + c[i+6] u) w^i, u^2 = -1, w^6 = 9 + u.  output = offset * x^exp_val. */
+typedef struct { uint64_t x[48], offset[48]; uint32_t exp_val[8]; uint64_t output[48]; } sbn_fq12_exp_io;
+/* Input record of Fq12ExpU64Stark, replaces `Fq12ExpU64IONative` (src/fields/fq12_u64/exp_u64.rs:85-90); exp_val < 2^64 - 2^32 + 1. */
+typedef struct { uint64_t x[48], offset[48]; uint64_t exp_val; uint64_t output[48]; } sbn_fq12_exp_u64_io;
 /* Input record of ModularStark: one row = two canonical Fq residues (src/modular/modular.rs:385-390). */
 typedef struct { uint64_t input0[4], input1[4]; } sbn_modular_io;
 

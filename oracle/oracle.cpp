@@ -6,6 +6,8 @@
 #include "stark.hpp"
 #include "air_modular.hpp"
 #include "air_g1.hpp"
+#include "air_g2.hpp"
+#include "air_fq12.hpp"
 #include "sample.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -28,8 +30,15 @@ struct AirHandle { int id; size_t num_io; std::unique_ptr<Air> air; };
 static ProverDebug g_dbg;
 static std::string g_err;
 
+// packed input records: identical to the sbn_*_io structs of include/starky_bn254_b200.h
 struct G1IoBlob { u64 x_x[4], x_y[4], off_x[4], off_y[4]; u32 exp[8]; u64 out_x[4], out_y[4]; };
+struct FqIoBlob { u64 x[4], off[4]; u32 exp[8]; u64 out[4]; };
+struct G2IoBlob { u64 x[16], off[16]; u32 exp[8]; u64 out[16]; };          // point = x.c0 x.c1 y.c0 y.c1
+struct Fq12IoBlob { u64 x[48], off[48]; u32 exp[8]; u64 out[48]; };        // 12 coefficients, MyFq12 order
+struct Fq12U64IoBlob { u64 x[48], off[48]; u64 exp; u64 out[48]; };
 static U256 mk(const u64* p) { U256 r; for (int i = 0; i < 4; i++) r.w[i] = p[i]; return r; }
+static G2Point mkg2(const u64* p) { return {mk(p), mk(p + 4), mk(p + 8), mk(p + 12)}; }
+static Fq12Words mk12(const u64* p) { Fq12Words w; for (int i = 0; i < 12; i++) w.c[i] = mk(p + 4 * i); return w; }
 
 extern "C" {
 const char* orc_last_error() { return g_err.c_str(); }
@@ -68,6 +77,10 @@ void* orc_air_create(int id, size_t num_io) {
   switch (id) {
     case AIR_MODULAR: h->air.reset(new ModularStark()); break;
     case AIR_G1_EXP: h->air.reset(new G1ExpStark(num_io)); break;
+    case AIR_FQ_EXP: h->air.reset(new FqExpStark(num_io)); break;
+    case AIR_G2_EXP: h->air.reset(new G2ExpStark(num_io)); break;
+    case AIR_FQ12_EXP: h->air.reset(new Fq12ExpStark(num_io)); break;
+    case AIR_FQ12_EXP_U64: h->air.reset(new Fq12ExpU64Stark(num_io)); break;
     default: delete h; g_err = "unsupported air"; return nullptr;
   }
   return h;
@@ -78,11 +91,32 @@ size_t orc_air_num_public_inputs(void* p) { return ((AirHandle*)p)->air->num_pub
 size_t orc_air_num_rows(void* p) { AirHandle* h = (AirHandle*)p; return h->id == AIR_MODULAR ? h->num_io : (h->id == AIR_FQ12_EXP_U64 ? 128 : 512) * h->num_io; }
 size_t orc_air_num_permutation_pairs(void* p) { return ((AirHandle*)p)->air->permutation_pairs().size(); }
 size_t orc_air_result_words(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_FQ_EXP: return 4; case AIR_G1_EXP: return 8; case AIR_G2_EXP: return 16; case AIR_FQ12_EXP: case AIR_FQ12_EXP_U64: return 48; } return 0; }
-size_t orc_air_io_size(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_MODULAR: return 64; case AIR_G1_EXP: return sizeof(G1IoBlob); } return 0; }
+size_t orc_air_io_size(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_MODULAR: return 64; case AIR_G1_EXP: return sizeof(G1IoBlob); case AIR_FQ_EXP: return sizeof(FqIoBlob); case AIR_G2_EXP: return sizeof(G2IoBlob);
+  case AIR_FQ12_EXP: return sizeof(Fq12IoBlob); case AIR_FQ12_EXP_U64: return sizeof(Fq12U64IoBlob); } return 0; }
 
 static std::vector<G1ExpIONative> g1_ios(const void* ios, size_t n) {
   const G1IoBlob* b = (const G1IoBlob*)ios; std::vector<G1ExpIONative> v(n);
   for (size_t i = 0; i < n; i++) { v[i].x = {mk(b[i].x_x), mk(b[i].x_y)}; v[i].offset = {mk(b[i].off_x), mk(b[i].off_y)}; memcpy(v[i].exp_val, b[i].exp, 32); v[i].output = {mk(b[i].out_x), mk(b[i].out_y)}; }
+  return v;
+}
+static std::vector<FqExpIONative> fq_ios(const void* ios, size_t n) {
+  const FqIoBlob* b = (const FqIoBlob*)ios; std::vector<FqExpIONative> v(n);
+  for (size_t i = 0; i < n; i++) { v[i].x = mk(b[i].x); v[i].offset = mk(b[i].off); memcpy(v[i].exp_val, b[i].exp, 32); v[i].output = mk(b[i].out); }
+  return v;
+}
+static std::vector<G2ExpIONative> g2_ios(const void* ios, size_t n) {
+  const G2IoBlob* b = (const G2IoBlob*)ios; std::vector<G2ExpIONative> v(n);
+  for (size_t i = 0; i < n; i++) { v[i].x = mkg2(b[i].x); v[i].offset = mkg2(b[i].off); memcpy(v[i].exp_val, b[i].exp, 32); v[i].output = mkg2(b[i].out); }
+  return v;
+}
+static std::vector<Fq12ExpIONative> fq12_ios(const void* ios, size_t n) {
+  const Fq12IoBlob* b = (const Fq12IoBlob*)ios; std::vector<Fq12ExpIONative> v(n);
+  for (size_t i = 0; i < n; i++) { v[i].x = mk12(b[i].x); v[i].offset = mk12(b[i].off); memcpy(v[i].exp_val, b[i].exp, 32); v[i].output = mk12(b[i].out); }
+  return v;
+}
+static std::vector<Fq12ExpU64IONative> fq12u64_ios(const void* ios, size_t n) {
+  const Fq12U64IoBlob* b = (const Fq12U64IoBlob*)ios; std::vector<Fq12ExpU64IONative> v(n);
+  for (size_t i = 0; i < n; i++) { v[i].x = mk12(b[i].x); v[i].offset = mk12(b[i].off); v[i].exp_val = b[i].exp; v[i].output = mk12(b[i].out); }
   return v;
 }
 // Trace generation.  out_cols: num_columns x num_rows column-major.  results (optional): per-io chain
@@ -99,6 +133,19 @@ int orc_generate_trace(void* p, const void* ios, size_t num_io, u64* out_cols, u
       std::vector<G1Point> res;
       cols = static_cast<G1ExpStark*>(h->air.get())->generate_trace(g1_ios(ios, num_io), &res);
       if (results) for (size_t i = 0; i < num_io; i++) { memcpy(results + 8 * i, res[i].x.w, 32); memcpy(results + 8 * i + 4, res[i].y.w, 32); }
+    } else if (h->id == AIR_FQ_EXP) {
+      std::vector<U256> res;
+      cols = static_cast<FqExpStark*>(h->air.get())->generate_trace(fq_ios(ios, num_io), &res);
+      if (results) for (size_t i = 0; i < num_io; i++) memcpy(results + 4 * i, res[i].w, 32);
+    } else if (h->id == AIR_G2_EXP) {
+      std::vector<G2Point> res;
+      cols = static_cast<G2ExpStark*>(h->air.get())->generate_trace(g2_ios(ios, num_io), &res);
+      if (results) for (size_t i = 0; i < num_io; i++) { memcpy(results + 16 * i, res[i].x0.w, 32); memcpy(results + 16 * i + 4, res[i].x1.w, 32); memcpy(results + 16 * i + 8, res[i].y0.w, 32); memcpy(results + 16 * i + 12, res[i].y1.w, 32); }
+    } else if (h->id == AIR_FQ12_EXP || h->id == AIR_FQ12_EXP_U64) {
+      std::vector<Fq12Words> res;
+      if (h->id == AIR_FQ12_EXP) cols = static_cast<Fq12ExpStark*>(h->air.get())->generate_trace(fq12_ios(ios, num_io), &res);
+      else cols = static_cast<Fq12ExpU64Stark*>(h->air.get())->generate_trace(fq12u64_ios(ios, num_io), &res);
+      if (results) for (size_t i = 0; i < num_io; i++) for (int k = 0; k < 12; k++) memcpy(results + 48 * i + 4 * k, res[i].c[k].w, 32);
     } else { g_err = "unsupported air"; return -1; }
     size_t n = cols[0].size();
     for (size_t c = 0; c < cols.size(); c++) for (size_t r = 0; r < n; r++) out_cols[c * n + r] = cols[c][r].v;
@@ -109,8 +156,14 @@ int orc_generate_public_inputs(void* p, const void* ios, size_t num_io, u64* out
   AirHandle* h = (AirHandle*)p;
   std::vector<GF> pi;
   if (h->id == AIR_MODULAR) return 0;
+  try {
   if (h->id == AIR_G1_EXP) pi = static_cast<G1ExpStark*>(h->air.get())->generate_public_inputs(g1_ios(ios, num_io));
+  else if (h->id == AIR_FQ_EXP) pi = static_cast<FqExpStark*>(h->air.get())->generate_public_inputs(fq_ios(ios, num_io));
+  else if (h->id == AIR_G2_EXP) pi = static_cast<G2ExpStark*>(h->air.get())->generate_public_inputs(g2_ios(ios, num_io));
+  else if (h->id == AIR_FQ12_EXP) pi = static_cast<Fq12ExpStark*>(h->air.get())->generate_public_inputs(fq12_ios(ios, num_io));
+  else if (h->id == AIR_FQ12_EXP_U64) pi = static_cast<Fq12ExpU64Stark*>(h->air.get())->generate_public_inputs(fq12u64_ios(ios, num_io));
   else { g_err = "unsupported air"; return -1; }
+  } catch (std::exception& e) { g_err = e.what(); return -2; }
   for (size_t i = 0; i < pi.size(); i++) out[i] = pi[i].v;
   return 0;
 }
@@ -191,6 +244,18 @@ int orc_time_sample(void* p, const void* ios, size_t num_io, const OrcConfig* c,
     size_t nrows = orc_air_num_rows(p);
     SampleTimes t = time_prove_sample(*h->air, nrows, to_cfg(c), shift);
     if (h->id == AIR_G1_EXP && ios) t.tracegen_ms = time_g1_tracegen_sample(*static_cast<G1ExpStark*>(h->air.get()), g1_ios(ios, num_io), shift);
+    if (h->id == AIR_G2_EXP && ios) {
+      auto* a = static_cast<G2ExpStark*>(h->air.get()); auto v = g2_ios(ios, num_io); G2Point r;
+      t.tracegen_ms = time_exp_tracegen_sample([&](size_t k) { a->generate_trace_for_one_block(v[k].x, v[k].offset, v[k].exp_val, &r); }, num_io, 512, a->num_range_check_cols, false, shift);
+    }
+    if (h->id == AIR_FQ_EXP && ios) {
+      auto* a = static_cast<FqExpStark*>(h->air.get()); auto v = fq_ios(ios, num_io); U256 r;
+      t.tracegen_ms = time_exp_tracegen_sample([&](size_t k) { a->generate_trace_for_one_block(v[k].x, v[k].offset, v[k].exp_val, &r); }, num_io, 512, a->num_range_check_cols, false, shift);
+    }
+    if (h->id == AIR_FQ12_EXP && ios) {
+      auto* a = static_cast<Fq12ExpStark*>(h->air.get()); auto v = fq12_ios(ios, num_io); Fq12Words r;
+      t.tracegen_ms = time_exp_tracegen_sample([&](size_t k) { a->generate_trace_for_one_block(v[k].x, v[k].offset, v[k].exp_val, &r); }, num_io, 512, a->num_range_check_cols, true, shift);
+    }
     out_ms[0] = t.tracegen_ms; out_ms[1] = t.commit_ms; out_ms[2] = t.zpoly_ms; out_ms[3] = t.quotient_ms; out_ms[4] = t.openings_ms; out_ms[5] = t.reduce_ms; out_ms[6] = t.fri_ms;
     return 0;
   } catch (std::exception& e) { g_err = e.what(); return -2; }

@@ -137,4 +137,21 @@ static inline double time_g1_tracegen_sample(const G1ExpStark& air, const std::v
   ms += tm.lap();
   return ms;
 }
+// Same for the other exponentiation AIRs: `block(k)` generates instance k's rows (serial loop, like the reference).
+template <class BlockFn> static inline double time_exp_tracegen_sample(BlockFn block, size_t num_io, size_t rows_per_io, size_t nrc, bool split, int shift) {
+  Timer tm;
+  size_t n = std::max<size_t>(1, num_io >> shift), N = num_io * rows_per_io;
+  tm.lap();
+  for (size_t k = 0; k < n; k++) block(k);
+  double ms = tm.lap();
+  Cols cols = random_cols(std::max<size_t>(1, nrc >> shift), N, 4, 65536);
+  size_t nc = cols.size();
+  std::vector<size_t> positions;
+  for (size_t i = 0; i < std::max<size_t>(1, (2 * num_io) >> shift); i++) positions.push_back(i * rows_per_io % N);
+  tm.lap();
+  { Cols c2(1, std::vector<GF>(N)); generate_pulse(c2, positions); }
+  if (split) generate_split_u16_range_check(0, nc, cols); else generate_u16_range_check(0, nc, cols);
+  ms += tm.lap();
+  return ms;
+}
 }  // namespace orc

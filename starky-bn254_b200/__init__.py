@@ -287,6 +287,26 @@ class G1ExpStark(_Stark):
     AIR = AIR_G1_EXP
 
 
+class FqExpStark(_Stark):
+    """reference src/fields/fq/exp.rs (inputs: packed sbn_fq_exp_io records)."""
+    AIR = AIR_FQ_EXP
+
+
+class G2ExpStark(_Stark):
+    """reference src/curves/g2/exp.rs (inputs: packed sbn_g2_exp_io records)."""
+    AIR = AIR_G2_EXP
+
+
+class Fq12ExpStark(_Stark):
+    """reference src/fields/fq12/exp.rs (inputs: packed sbn_fq12_exp_io records, MyFq12 coefficient order)."""
+    AIR = AIR_FQ12_EXP
+
+
+class Fq12ExpU64Stark(_Stark):
+    """reference src/fields/fq12_u64/exp_u64.rs (inputs: packed sbn_fq12_exp_u64_io records)."""
+    AIR = AIR_FQ12_EXP_U64
+
+
 def prove(stark, config, trace, public_inputs, timing=None):
     """`starky::prover::prove(stark, &config, trace_poly_values, public_inputs, &mut timing)` on the GPU."""
     ctx = trace.ctx

@@ -11,7 +11,8 @@
 
 enum SegKind {
   SEG_SPLIT_RANGE_CHECK, SEG_MODULAR_CORE, SEG_G1_CORE, SEG_FLAGS, SEG_G1_ADD, SEG_G1_DOUBLE, SEG_PERIODIC_PULSE, SEG_PULSE,
-  SEG_U16_RANGE_CHECK, SEG_PERMUTATION
+  SEG_U16_RANGE_CHECK, SEG_PERMUTATION,
+  SEG_FQ_CORE, SEG_FQ_MUL, SEG_G2_CORE, SEG_G2_ADD, SEG_G2_DOUBLE, SEG_FQ12_CORE, SEG_FQ12_MUL, SEG_FLAGS_U64
 };
 struct Segment { SegKind kind; int p0, p1, p2, p3; size_t num_constraints; };
 

@@ -60,25 +60,41 @@ HD u64 bn254_limb(int i) {
   return m[i];
 }
 
-// Description of the input polynomial of a modular gadget:  in(x) = s1*A(x)*B(x) - s2*C(x)*D(x) - E(x)
-// with A..E 16-limb columns (local row).  a/b/c/d/e are arrays of 16 values already loaded.
+// Description of the input polynomial of a modular gadget:
+//   in(x) = sum_t scale[t] * A[t](x) * B[t](x)  -  E(x)  -  E2(x)          (t < nprod <= 4)
+// with A, B, E, E2 16-limb columns of the local row already loaded, scale a small signed integer; or, when
+// `direct` is set, the 31 coefficients are read from memory (direct[k * direct_stride]) -- used for the Fq12
+// product, whose limb polynomial is produced by a separate kernel.  Field arithmetic is exact, so any
+// association of the sums yields the same canonical element as the reference's `pol_*` call sequence.
 struct ModInput {
-  const F* A; const F* B; u64 s1;
-  const F* C; const F* D; u64 s2;   // C == nullptr: no second product
-  const F* E;                        // nullptr: none.  16 coefficients.
-  bool e_is_sum;                     // E given as E1 + E2 (E2 below)
-  const F* E2;
+  int nprod;
+  const F* A[4]; const F* B[4]; int scale[4];
+  const F* E; const F* E2;
+  const u64* direct; size_t direct_stride;
 };
+HD ModInput mod_input1(const F* a, const F* b, int s, const F* e = nullptr, const F* e2 = nullptr) {
+  ModInput in; in.nprod = 1; in.A[0] = a; in.B[0] = b; in.scale[0] = s; in.E = e; in.E2 = e2; in.direct = nullptr; in.direct_stride = 0;
+  for (int t = 1; t < 4; t++) { in.A[t] = nullptr; in.B[t] = nullptr; in.scale[t] = 0; }
+  return in;
+}
+HD ModInput mod_input2(const F* a0, const F* b0, int s0, const F* a1, const F* b1, int s1, const F* e = nullptr, const F* e2 = nullptr) {
+  ModInput in = mod_input1(a0, b0, s0, e, e2); in.nprod = 2; in.A[1] = a1; in.B[1] = b1; in.scale[1] = s1; return in;
+}
+HD ModInput mod_input4(const F* a0, const F* b0, int s0, const F* a1, const F* b1, int s1, const F* a2, const F* b2, int s2, const F* a3, const F* b3, int s3) {
+  ModInput in = mod_input2(a0, b0, s0, a1, b1, s1); in.nprod = 4; in.A[2] = a2; in.B[2] = b2; in.scale[2] = s2; in.A[3] = a3; in.B[3] = b3; in.scale[3] = s3; return in;
+}
+HD ModInput mod_input_direct(const u64* p, size_t stride) { ModInput in = mod_input1(nullptr, nullptr, 0); in.nprod = 0; in.direct = p; in.direct_stride = stride; return in; }
 HD F mod_input_coeff(const ModInput& in, int k) {
+  if (in.direct) return F(in.direct[(size_t)k * in.direct_stride]);
   F acc;
   int lo = k > 15 ? k - 15 : 0, hi = k < 15 ? k : 15;
-  for (int i = lo; i <= hi; i++) acc = acc + in.A[i] * in.B[k - i];
-  if (in.s1 != 1) acc = acc * F(in.s1);
-  if (in.C) {
-    F acc2;
-    for (int i = lo; i <= hi; i++) acc2 = acc2 + in.C[i] * in.D[k - i];
-    if (in.s2 != 1) acc2 = acc2 * F(in.s2);
-    acc = acc - acc2;
+  for (int t = 0; t < in.nprod; t++) {
+    F p;
+    for (int i = lo; i <= hi; i++) p = p + in.A[t][i] * in.B[t][k - i];
+    int sc = in.scale[t];
+    int mag = sc < 0 ? -sc : sc;
+    if (mag != 1) p = p * F((u64)mag);
+    acc = sc < 0 ? acc - p : acc + p;
   }
   if (in.E && k < 16) { acc = acc - in.E[k]; if (in.E2) acc = acc - in.E2[k]; }
   return acc;
@@ -235,7 +251,7 @@ HD void eval_split_u16_range_check(QPoint& q, int main_col, int t0, int ntargets
 HD void eval_modular_stark_core(QPoint& q) {
   F in0[16], in1[16], out[16];
   load16(q, 0, in0); load16(q, 16, in1); load16(q, 32, out);
-  ModInput in = {in0, in1, 1, nullptr, nullptr, 1, nullptr, false, nullptr};
+  ModInput in = mod_input1(in0, in1, 1);
   F filter = q.lv(48 + 95 + 1);
   eval_modular_op(q, filter, in, out, 48, 48 + 95);
 }
@@ -257,12 +273,12 @@ HD void eval_g1_tail(QPoint& q, F filter, int o, const F* lambda, const F* x1, c
   F new_x[16], new_y[16];
   load16(q, o + G1O_NEW_X, new_x); load16(q, o + G1O_NEW_Y, new_y);
   // new_x_input = lambda^2 - (x1 + x2)
-  ModInput inx = {lambda, lambda, 1, nullptr, nullptr, 1, x1, true, x2};
+  ModInput inx = mod_input1(lambda, lambda, 1, x1, x2);
   eval_modular_op(q, filter, inx, new_x, o + G1O_AUX_X, o + G1O_SIGN_X);
   // new_y_input = lambda * (x1 - new_x) - y1
   F d[16];
   for (int i = 0; i < 16; i++) d[i] = x1[i] - new_x[i];
-  ModInput iny = {lambda, d, 1, nullptr, nullptr, 1, y1, false, nullptr};
+  ModInput iny = mod_input1(lambda, d, 1, y1);
   eval_modular_op(q, filter, iny, new_y, o + G1O_AUX_Y, o + G1O_SIGN_Y);
 }
 // reference src/curves/g1/muladd.rs:179-230 `eval_g1_add`: 33 + 66 + 66 constraints.  a at cols 0..31, b at 32..63.
@@ -271,7 +287,7 @@ HD void eval_g1_add(QPoint& q, F filter, int o) {
   load16(q, 0, ax); load16(q, 16, ay); load16(q, 32, bx); load16(q, 48, by); load16(q, o + G1O_LAMBDA, lambda);
   for (int i = 0; i < 16; i++) { dx[i] = bx[i] - ax[i]; dy[i] = by[i] - ay[i]; }
   // zero_pol = lambda * delta_x - delta_y
-  ModInput inz = {lambda, dx, 1, nullptr, nullptr, 1, dy, false, nullptr};
+  ModInput inz = mod_input1(lambda, dx, 1, dy);
   eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
   eval_g1_tail(q, filter, o, lambda, ax, bx, ay);
 }
@@ -280,7 +296,7 @@ HD void eval_g1_double(QPoint& q, F filter, int o) {
   F x[16], y[16], lambda[16];
   load16(q, 0, x); load16(q, 16, y); load16(q, o + G1O_LAMBDA, lambda);
   // zero_pol = 2*lambda*y - 3*x*x
-  ModInput inz = {lambda, y, 2, x, x, 3, nullptr, false, nullptr};
+  ModInput inz = mod_input2(lambda, y, 2, x, x, -3);
   eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
   eval_g1_tail(q, filter, o, lambda, x, x, y);
 }
@@ -320,4 +336,210 @@ HD void eval_g1_exp_core(QPoint& q, int num_io) {
   for (int i = 0; i < 16; i++) q.transition(f2 * (q.nv(48 + i) - q.lv(out_o + G1O_NEW_Y + i)));
   // neither: next = current
   for (int i = 0; i < 64; i++) q.transition(f3 * (q.nv(i) - q.lv(i)));
+}
+
+// ---- generic exponentiation-AIR core for the AIRs whose public inputs are u32 limbs (Fq, G1, G2) ----
+// reference src/fields/fq/exp.rs:289-359, src/curves/g1/exp.rs:340-461, src/curves/g2/exp.rs:354-472:
+// is_final constraint, public-input binding, a/b transitions.  The row starts with a (G groups of 16 limbs)
+// and b (G groups); `newv` is the column of the G-group value the operation produces (Fq: output, G1/G2:
+// new_x | new_y); per-io public inputs are x[G][8] offset[G][8] exp_val[8] output[G][8].
+// 1 + (3G + 1) * 8 * num_io + 3 * 32 * G constraints.  G = 2 is exactly eval_g1_exp_core.
+template <int G> HD void eval_exp_core_u32(QPoint& q, int num_io, int newv, int sf) {
+  const int start_pulses = sf + 14 + 2;
+  const F one(1), base(1ULL << 16);
+  F is_add = q.lv(sf + 4), is_double = q.lv(sf + 2), is_final = q.lv(sf), is_not_final = one - is_final;
+  F sum_is_output;
+  for (int i = 1; i < 2 * num_io; i += 2) sum_is_output = sum_is_output + q.lv(start_pulses + 2 + 2 * i);
+  q.constraint(is_final - sum_is_output);
+  F va[G][8], vb[G][8], ve[8];
+  for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) {
+    va[g][j] = q.lv(16 * g + 2 * j) + base * q.lv(16 * g + 2 * j + 1);
+    vb[g][j] = q.lv(16 * (G + g) + 2 * j) + base * q.lv(16 * (G + g) + 2 * j + 1);
+  }
+  for (int j = 0; j < 8; j++) ve[j] = q.lv(sf + 6 + j);
+  ve[0] = ve[0] * F(2) + is_add;
+  const int io_len = (3 * G + 1) * 8;
+  for (int i = 0; i < num_io; i++) {
+    F is_in = q.lv(start_pulses + 2 + 4 * i), is_out = q.lv(start_pulses + 4 + 4 * i);
+    const u64* io = q.pi + (size_t)io_len * i;
+    for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * g + j]) - va[g][j]));
+    for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * (G + g) + j]) - vb[g][j]));
+    for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) q.constraint(is_out * (F(io[8 * (2 * G + 1 + g) + j]) - vb[g][j]));
+    for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * 2 * G + j]) - ve[j]));
+  }
+  const int W = 16 * G;
+  F f1 = is_not_final * is_double, f2 = is_not_final * is_add, f3 = is_not_final * (one - is_double - is_add);
+  for (int i = 0; i < W; i++) q.transition(f1 * (q.nv(i) - q.lv(newv + i)));
+  for (int i = 0; i < W; i++) q.transition(f1 * (q.nv(W + i) - q.lv(W + i)));
+  for (int i = 0; i < W; i++) q.transition(f2 * (q.nv(i) - q.lv(i)));
+  for (int i = 0; i < W; i++) q.transition(f2 * (q.nv(W + i) - q.lv(newv + i)));
+  for (int i = 0; i < 2 * W; i++) q.transition(f3 * (q.nv(i) - q.lv(i)));
+}
+
+// ---- Fq (reference src/fields/fq/mul.rs:69-87 `eval_fq_mul`): a at 0, b at 16, FqOutput at 32 = output16 | aux95 | sign ----
+HD void eval_fq_mul(QPoint& q, F filter, bool square) {
+  F a[16], b[16], out[16];
+  load16(q, 0, a); load16(q, square ? 0 : 16, b); load16(q, 32, out);
+  ModInput in = mod_input1(a, b, 1);
+  eval_modular_op(q, filter, in, out, 48, 48 + 95);
+}
+
+// ---- G2 (reference src/curves/g2/muladd.rs) ----
+// Row: a_x(c0,c1) a_y b_x b_y = columns 0..127; G2Output block at o = 128:
+// lambda32 new_x32 new_y32 | aux_zero 2x79 | aux 4x95 | sign_zero x2 | sign x4   (muladd.rs:56-80)
+#define G2O_LAMBDA 0
+#define G2O_NEW_X 32
+#define G2O_NEW_Y 64
+#define G2O_AUX_ZERO 96
+#define G2O_AUX 254
+#define G2O_SIGN_ZERO 634
+#define G2O_SIGN 636
+// shared tail of eval_g2_add / eval_g2_double (muladd.rs:233-260 / :446-471): x1, y1 are the "a" operands
+HD void eval_g2_tail(QPoint& q, F filter, int o, const F* l0, const F* l1, const F* x1c0, const F* x1c1, const F* x2c0, const F* x2c1, const F* y1c0, const F* y1c1) {
+  F nx0[16], nx1[16], ny0[16], ny1[16];
+  load16(q, o + G2O_NEW_X, nx0); load16(q, o + G2O_NEW_X + 16, nx1);
+  // new_x_input = lambda^2 - (x1 + x2):  c0 = l0 l0 - l1 l1, c1 = l0 l1 + l1 l0
+  { ModInput in = mod_input2(l0, l0, 1, l1, l1, -1, x1c0, x2c0); eval_modular_op(q, filter, in, nx0, o + G2O_AUX, o + G2O_SIGN); }
+  { ModInput in = mod_input1(l0, l1, 2, x1c1, x2c1); eval_modular_op(q, filter, in, nx1, o + G2O_AUX + 95, o + G2O_SIGN + 1); }
+  // new_y_input = lambda * (x1 - new_x) - y1
+  F d0[16], d1[16];
+  for (int i = 0; i < 16; i++) { d0[i] = x1c0[i] - nx0[i]; d1[i] = x1c1[i] - nx1[i]; }
+  load16(q, o + G2O_NEW_Y, ny0); load16(q, o + G2O_NEW_Y + 16, ny1);
+  { ModInput in = mod_input2(l0, d0, 1, l1, d1, -1, y1c0); eval_modular_op(q, filter, in, ny0, o + G2O_AUX + 190, o + G2O_SIGN + 2); }
+  { ModInput in = mod_input2(l0, d1, 1, l1, d0, 1, y1c1); eval_modular_op(q, filter, in, ny1, o + G2O_AUX + 285, o + G2O_SIGN + 3); }
+}
+// reference src/curves/g2/muladd.rs:416-472 `eval_g2_add`: 2*33 + 4*66 = 330 constraints
+HD void eval_g2_add(QPoint& q, F filter, int o) {
+  F ax0[16], ax1[16], ay0[16], ay1[16], bx0[16], bx1[16], l0[16], l1[16], dx0[16], dx1[16], dy0[16], dy1[16];
+  load16(q, 0, ax0); load16(q, 16, ax1); load16(q, 32, ay0); load16(q, 48, ay1); load16(q, 64, bx0); load16(q, 80, bx1);
+  load16(q, o + G2O_LAMBDA, l0); load16(q, o + G2O_LAMBDA + 16, l1);
+  for (int i = 0; i < 16; i++) { dx0[i] = bx0[i] - ax0[i]; dx1[i] = bx1[i] - ax1[i]; dy0[i] = q.lv(96 + i) - ay0[i]; dy1[i] = q.lv(112 + i) - ay1[i]; }
+  // zero_pol = lambda * delta_x - delta_y
+  { ModInput in = mod_input2(l0, dx0, 1, l1, dx1, -1, dy0); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO, o + G2O_SIGN_ZERO); }
+  { ModInput in = mod_input2(l0, dx1, 1, l1, dx0, 1, dy1); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO + 79, o + G2O_SIGN_ZERO + 1); }
+  eval_g2_tail(q, filter, o, l0, l1, ax0, ax1, bx0, bx1, ay0, ay1);
+}
+// reference src/curves/g2/muladd.rs:203-261 `eval_g2_double`: 330 constraints
+HD void eval_g2_double(QPoint& q, F filter, int o) {
+  F x0[16], x1[16], y0[16], y1[16], l0[16], l1[16];
+  load16(q, 0, x0); load16(q, 16, x1); load16(q, 32, y0); load16(q, 48, y1);
+  load16(q, o + G2O_LAMBDA, l0); load16(q, o + G2O_LAMBDA + 16, l1);
+  // zero_pol = 2 * lambda * y - 3 * x * x
+  { ModInput in = mod_input4(l0, y0, 2, l1, y1, -2, x0, x0, -3, x1, x1, 3); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO, o + G2O_SIGN_ZERO); }
+  { ModInput in = mod_input4(l0, y1, 2, l1, y0, 2, x0, x1, -3, x1, x0, -3); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO + 79, o + G2O_SIGN_ZERO + 1); }
+  eval_g2_tail(q, filter, o, l0, l1, x0, x1, x0, x1, y0, y1);
+}
+
+// ---- Fq12 (reference src/fields/fq12/mul.rs, src/fields/fq12/exp.rs, src/fields/fq12_u64) ----
+// Row: a (12x16) at 0, b at 192, Fq12Output at 384 = output 12x16 | aux 12x95 | sign x12   (mul.rs:219-231)
+#define FQ12O_AUX 192
+#define FQ12O_SIGN (192 + 12 * 95)
+// reference src/fields/fq12/mul.rs:254-275 `eval_fq12_mul`: 12 * 66 constraints.  `prod` holds the limb polynomial of
+// pol_mul_fq12(x, y, 9) for this point: coefficient k of output i at prod[(i * 31 + k) * prod_stride].
+HD void eval_fq12_mul(QPoint& q, F filter, const u64* prod, size_t prod_stride) {
+  const int o = 384;
+  for (int i = 0; i < 12; i++) {
+    F out[16];
+    load16(q, o + 16 * i, out);
+    ModInput in = mod_input_direct(prod + (size_t)i * 31 * prod_stride, prod_stride);
+    eval_modular_op(q, filter, in, out, o + FQ12O_AUX + 95 * i, o + FQ12O_SIGN + i);
+  }
+}
+// pol_mul_fq12(x, y, 9) (reference src/fields/fq12/mul.rs:24-87): the 31 limbs of output coefficient `oi` (flat MyFq12
+// order) for x at column xa and y at column ya of the local row, accumulated while the contributing (x_i, y_j)
+// limb pairs stream through.
+//   re[m] = sum_{i+j=m} (x_i y_j - x_{i+6} y_{j+6}),  im[m] = sum_{i+j=m} (x_i y_{j+6} + x_{i+6} y_j)
+//   out[i] = re[i] + 9 re[i+6] - im[i+6],  out[i+6] = im[i] + re[i+6] + 9 im[i+6]   (i < 5);  out[5] = re[5], out[11] = im[5]
+HD void fq12_product_acc(const QPoint& q, int xa, int ya, int oi, F* acc /*31*/) {
+#pragma unroll
+  for (int k = 0; k < 31; k++) acc[k] = F();
+  const bool imag = oi >= 6; const int i0 = imag ? oi - 6 : oi;
+  // terms: (m, part, weight): part 0 = re, 1 = im
+  for (int term = 0; term < 3; term++) {
+    int m, part, w;
+    if (term == 0) { m = i0; part = imag ? 1 : 0; w = 1; }
+    else if (i0 == 5) break;
+    else if (term == 1) { m = i0 + 6; part = 0; w = imag ? 1 : 9; }
+    else { m = i0 + 6; part = 1; w = imag ? 9 : -1; }
+    for (int i = 0; i < 6; i++) {
+      const int j = m - i;
+      if (j < 0 || j > 5) continue;
+      for (int half = 0; half < 2; half++) {
+        // re: (x_i, y_j, +), (x_{i+6}, y_{j+6}, -);  im: (x_i, y_{j+6}, +), (x_{i+6}, y_j, +)
+        const int xi = half ? i + 6 : i;
+        const int yj = part == 0 ? (half ? j + 6 : j) : (half ? j : j + 6);
+        const bool neg = (part == 0 && half == 1) != (w < 0);
+        F x[16], y[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) { x[t] = q.lv(xa + 16 * xi + t); y[t] = q.lv(ya + 16 * yj + t); }
+        if (w == 9 || w == -9) {
+#pragma unroll
+          for (int t = 0; t < 16; t++) x[t] = x[t] * F(9);
+        }
+        if (neg) {
+#pragma unroll
+          for (int t = 0; t < 16; t++) x[t] = -x[t];
+        }
+#pragma unroll
+        for (int s = 0; s < 16; s++)
+#pragma unroll
+          for (int t = 0; t < 16; t++) acc[s + t] = acc[s + t] + x[s] * y[t];
+      }
+    }
+  }
+}
+// reference src/fields/fq12/exp.rs:340-393 (u64 variant: src/fields/fq12_u64/exp_u64.rs:331-383): is_final, public inputs
+// (u16 limbs: x[12][16] offset[12][16] exp output[12][16]), transitions.  1 + io_len * num_io + 6 * 192 constraints.
+HD void eval_fq12_exp_core(QPoint& q, int num_io, int sf, bool u64_variant) {
+  const int nflags = u64_variant ? 6 : 14;
+  const int start_pulses = sf + nflags + (u64_variant ? 0 : 2);
+  const int is_sq_c = u64_variant ? sf + 1 : sf + 2, is_mul_c = u64_variant ? sf + 3 : sf + 4;
+  const int io_len = u64_variant ? 577 : 584, out_off = u64_variant ? 385 : 392;
+  const F one(1);
+  F is_mul = q.lv(is_mul_c), is_sq = q.lv(is_sq_c), is_final = q.lv(sf), is_not_final = one - is_final;
+  F sum_is_output;
+  for (int i = 1; i < 2 * num_io; i += 2) sum_is_output = sum_is_output + q.lv(start_pulses + 2 + 2 * i);
+  q.constraint(is_final - sum_is_output);
+  for (int i = 0; i < num_io; i++) {
+    F is_in = q.lv(start_pulses + 2 + 4 * i), is_out = q.lv(start_pulses + 4 + 4 * i);
+    const u64* io = q.pi + (size_t)io_len * i;
+    for (int c = 0; c < 12; c++) {
+      for (int j = 0; j < 16; j++) q.constraint(is_in * (F(io[16 * c + j]) - q.lv(16 * c + j)));
+      for (int j = 0; j < 16; j++) q.constraint(is_in * (F(io[192 + 16 * c + j]) - q.lv(192 + 16 * c + j)));
+      for (int j = 0; j < 16; j++) q.constraint(is_out * (F(io[out_off + 16 * c + j]) - q.lv(192 + 16 * c + j)));
+    }
+    if (u64_variant) {
+      q.constraint(is_in * (F(io[384]) - (q.lv(sf + 5) * F(2) + is_mul)));
+    } else {
+      for (int j = 0; j < 8; j++) {
+        F limb = q.lv(sf + 6 + j);
+        if (j == 0) limb = limb * F(2) + is_mul;
+        q.constraint(is_in * (F(io[384 + j]) - limb));
+      }
+    }
+  }
+  F f1 = is_not_final * is_sq, f2 = is_not_final * is_mul, f3 = is_not_final * (one - is_sq - is_mul);
+  for (int i = 0; i < 192; i++) q.transition(f1 * (q.nv(i) - q.lv(384 + i)));
+  for (int i = 0; i < 192; i++) q.transition(f1 * (q.nv(192 + i) - q.lv(192 + i)));
+  for (int i = 0; i < 192; i++) q.transition(f2 * (q.nv(i) - q.lv(i)));
+  for (int i = 0; i < 192; i++) q.transition(f2 * (q.nv(192 + i) - q.lv(384 + i)));
+  for (int i = 0; i < 384; i++) q.transition(f3 * (q.nv(i) - q.lv(i)));
+}
+// reference src/fields/fq12_u64/flags_u64.rs:96-139 `eval_flags_u64`: 9 constraints.  is_final a b filtered_bit bit val
+HD void eval_flags_u64(QPoint& q, int sf) {
+  const int a = sf + 1, b = sf + 2, fbit = sf + 3, bit_c = sf + 4, val = sf + 5;
+  const F one(1);
+  q.first_row(q.lv(a));
+  q.first_row(q.lv(b) - one);
+  F bit = q.lv(bit_c);
+  q.constraint(bit * bit - bit);
+  q.constraint(bit * q.lv(b) - q.lv(fbit));
+  q.transition(q.lv(a) + q.nv(a) - one);
+  q.transition(q.lv(b) + q.nv(b) - one);
+  F first_limb = q.lv(val), next_first_limb = q.nv(val), next_bit = q.nv(bit_c), is_split = q.lv(a), is_final = q.lv(sf);
+  F is_not_final = one - is_final;
+  q.transition(is_not_final * is_split * (first_limb - F(2) * next_first_limb - next_bit));
+  F is_not_split = one - is_split;
+  q.transition(is_not_split * (next_bit - bit));
+  q.transition(is_not_final * is_not_split * (first_limb - next_first_limb));
 }

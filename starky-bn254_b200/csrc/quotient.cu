@@ -65,7 +65,33 @@ HD void eval_segment(const QArgs& a, const Segment& s, size_t idx, QPoint& q) {
     case SEG_PULSE: eval_pulse(q, s.p0, s.p1, s.p2); break;
     case SEG_U16_RANGE_CHECK: eval_u16_range_check(q, s.p0, s.p1); break;
     case SEG_PERMUTATION: eval_permutation_checks(a, idx, q); break;
+    case SEG_FQ_CORE: eval_exp_core_u32<1>(q, s.p0, s.p1, s.p2); break;
+    case SEG_G2_CORE: eval_exp_core_u32<4>(q, s.p0, s.p1, s.p2); break;
+    case SEG_FQ_MUL: eval_fq_mul(q, q.lv(s.p0), s.p1 != 0); break;
+    case SEG_G2_ADD: eval_g2_add(q, q.lv(s.p1), s.p0); break;
+    case SEG_G2_DOUBLE: eval_g2_double(q, q.lv(s.p1), s.p0); break;
+    case SEG_FQ12_CORE: eval_fq12_exp_core(q, s.p0, s.p1, s.p2 != 0); break;
+    case SEG_FQ12_MUL: eval_fq12_mul(q, q.lv(s.p0), a.scratch + idx, size_t(2) << a.logn); break;
+    case SEG_FLAGS_U64: eval_flags_u64(q, s.p0); break;
   }
+}
+
+// Limb polynomial of pol_mul_fq12(x, y, 9) (reference src/fields/fq12/mul.rs:24-87) at every quotient point, for the
+// SEG_FQ12_MUL segment: prod[(oi * 31 + k) * 2N + idx].  One thread per (point, output coefficient oi); the 31
+// coefficients are accumulated in registers while the contributing (x_i, y_j) limb pairs stream through.
+//   out[i]   = re[i] + 9 re[i+6] - im[i+6],  out[i+6] = im[i] + re[i+6] + 9 im[i+6]  (i < 5);  out[5] = re[5], out[11] = im[5]
+//   re[m] = sum_{i+j=m} (x_i y_j - x_{i+6} y_{j+6}),  im[m] = sum_{i+j=m} (x_i y_{j+6} + x_{i+6} y_j)
+__global__ void __launch_bounds__(128) k_fq12_products(QArgs a, int xa, int ya, u64* __restrict__ prod) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t N2 = size_t(2) << a.logn;
+  if (idx >= N2) return;
+  const int oi = blockIdx.y;
+  QPoint q;
+  qpoint_begin(a, idx, q);
+  F acc[31];
+  fq12_product_acc(q, xa, ya, oi, acc);
+#pragma unroll
+  for (int k = 0; k < 31; k++) prod[((size_t)oi * 31 + k) * N2 + idx] = acc[k].v;
 }
 
 template <int KIND> __global__ void __launch_bounds__(128) k_segment(QArgs a, Segment s) {
@@ -83,16 +109,25 @@ static const char* seg_name(SegKind k) {
     case SEG_SPLIT_RANGE_CHECK: return "q_split_range_check"; case SEG_MODULAR_CORE: return "q_modular_core"; case SEG_G1_CORE: return "q_g1_core";
     case SEG_FLAGS: return "q_flags"; case SEG_G1_ADD: return "q_g1_add"; case SEG_G1_DOUBLE: return "q_g1_double"; case SEG_PERIODIC_PULSE: return "q_periodic_pulse";
     case SEG_PULSE: return "q_pulse"; case SEG_U16_RANGE_CHECK: return "q_u16_range_check"; case SEG_PERMUTATION: return "q_permutation";
+    case SEG_FQ_CORE: return "q_fq_core"; case SEG_FQ_MUL: return "q_fq_mul"; case SEG_G2_CORE: return "q_g2_core"; case SEG_G2_ADD: return "q_g2_add";
+    case SEG_G2_DOUBLE: return "q_g2_double"; case SEG_FQ12_CORE: return "q_fq12_core"; case SEG_FQ12_MUL: return "q_fq12_mul"; case SEG_FLAGS_U64: return "q_flags_u64";
   }
   return "q_other";
 }
 static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
-  KScope ks(ctx, seg_name(s.kind));
   unsigned blocks = (unsigned)(((size_t(2) << a.logn) + 127) / 128);
+  if (s.kind == SEG_FQ12_MUL) {   // x = a; y = a (square) or b (mul): columns 0 / 192 of the row
+    KScope kp(ctx, "q_fq12_products");
+    k_fq12_products<<<dim3(blocks, 12), 128, 0, ctx->stream>>>(a, 0, s.p1 ? 0 : 192, a.scratch);
+    LAUNCH_CHECK(ctx);
+  }
+  KScope ks(ctx, seg_name(s.kind));
 #define SEGCASE(K) case K: k_segment<K><<<blocks, 128, 0, ctx->stream>>>(a, s); break;
   switch (s.kind) {
     SEGCASE(SEG_SPLIT_RANGE_CHECK) SEGCASE(SEG_MODULAR_CORE) SEGCASE(SEG_G1_CORE) SEGCASE(SEG_FLAGS) SEGCASE(SEG_G1_ADD)
     SEGCASE(SEG_G1_DOUBLE) SEGCASE(SEG_PERIODIC_PULSE) SEGCASE(SEG_PULSE) SEGCASE(SEG_U16_RANGE_CHECK) SEGCASE(SEG_PERMUTATION)
+    SEGCASE(SEG_FQ_CORE) SEGCASE(SEG_FQ_MUL) SEGCASE(SEG_G2_CORE) SEGCASE(SEG_G2_ADD) SEGCASE(SEG_G2_DOUBLE) SEGCASE(SEG_FQ12_CORE) SEGCASE(SEG_FQ12_MUL)
+    SEGCASE(SEG_FLAGS_U64)
   }
 #undef SEGCASE
   LAUNCH_CHECK(ctx);
@@ -156,6 +191,9 @@ void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_
     a.perm_lhs = d_lhs; a.perm_rhs = d_rhs; a.perm_gamma = d_gamma; a.perm_batch = perm.batch_size; a.nz = (int)perm.nz();
     segs.push_back({SEG_PERMUTATION, 0, 0, 0, 0, 2 * perm.nz()});
   }
+  DevBuf<u64> scratch;
+  for (const Segment& s : segs) if (s.kind == SEG_FQ12_MUL && !scratch.p) scratch = DevBuf<u64>(ctx, (size_t)12 * 31 * 2 * N);
+  a.scratch = scratch.p;
   bool first = true;
   for (const Segment& s : segs) {
     a.first = first ? 1 : 0;

@@ -27,6 +27,7 @@ struct QArgs {
   int first;                                 // first segment: accumulators start from zero
   // permutation segment
   const u32* perm_lhs; const u32* perm_rhs; const u64* perm_gamma; int perm_batch; int nz;
+  u64* scratch;                              // Fq12 product limb polynomials [12*31][2N] (SEG_FQ12_MUL only)
 };
 
 // Evaluates every constraint of `air` (+ the permutation checks) on the size-2N quotient coset and

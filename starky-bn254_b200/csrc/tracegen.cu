@@ -278,6 +278,275 @@ static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   if (h_results) for (size_t i = 0; i < n; i++) memcpy(h_results + i * 8, res.data() + i * 16, 64);
 }
 
+
+// Common tail of every exponentiation AIR (e.g. reference src/curves/g1/exp.rs:299-312): periodic-pulse witness,
+// io pulses, range-check lookups.
+struct ExpTail { int sf, nflags; bool periodic; int rows_per_io; int t0, ntargets; bool split; };
+static void generate_exp_tail(sbn_ctx* ctx, const AirDesc& air, u64* d_cols, const ExpTail& t) {
+  const size_t n = air.num_io, N = air.num_rows;
+  int col = t.sf + t.nflags;
+  if (t.periodic) {
+    Inv64 inv;
+    for (int c = 0; c < 64; c++) inv.v[c] = c == 63 ? 0 : gl_inv(gl_sub((u64)c, 63));
+    k_periodic_pulse<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_cols + (size_t)col * N, d_cols + (size_t)(col + 1) * N, N, inv); LAUNCH_CHECK(ctx);
+    col += 2;
+  }
+  DevBuf<u64> invtab(ctx, N);
+  k_inverse_table<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(invtab, N); LAUNCH_CHECK(ctx);
+  { KScope ksp(ctx, "io_pulses");
+    k_io_pulses<<<dim3((unsigned)((N + 255) / 256), (unsigned)(2 * n)), 256, 0, ctx->stream>>>(d_cols + (size_t)col * N, N, t.rows_per_io, invtab); LAUNCH_CHECK(ctx); }
+  const int lookups = col + 1 + 4 * (int)n;
+  if (t.split) generate_split_u16_range_check_cols(ctx, d_cols, N, t.t0, t.ntargets, lookups);
+  else generate_u16_range_check_cols(ctx, d_cols, N, t.t0, t.ntargets, lookups);
+}
+static void check_chain_error(sbn_ctx* ctx, int* d_err, const char* what) {
+  int h_err = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  SBN_REQUIRE(h_err != 2, "input coordinate is not a canonical Fq residue");
+  SBN_REQUIRE(!h_err, what);
+}
+template <class T> static const T* stage_ios(sbn_ctx* ctx, const void* ios, bool on_device, size_t n, DevBuf<T>& buf) {
+  if (on_device) return (const T*)ios;
+  buf = DevBuf<T>(ctx, n);
+  CUDA_CHECK(cudaMemcpyAsync(buf, ios, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return buf;
+}
+
+// ---------------- FqExpStark (reference src/fields/fq/exp.rs) ----------------
+// chain values as canonical words: A[k] = x^(2^k), B[k] = offset * prod_{j<k, bit_j} A[j], k = 0..256
+__global__ void __launch_bounds__(32) k_fq_chain(const sbn_fq_exp_io* __restrict__ ios, size_t num_io, u32* __restrict__ chain /* [io][2][257][8] */, int* __restrict__ err) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= num_io) return;
+  const sbn_fq_exp_io& io = ios[i];
+  u32 w[8];
+  u64x4_to_words((const u64*)io.x, w); if (fq_geq_p(w)) *err = 2; Fq A = fq_from_words(w);
+  u64x4_to_words((const u64*)io.offset, w); if (fq_geq_p(w)) *err = 2; Fq B = fq_from_words(w);
+  u32* ca = chain + i * 2 * 257 * 8; u32* cb = ca + 257 * 8;
+  for (int k = 0; k <= 256; k++) {
+    fq_to_words(A, ca + k * 8); fq_to_words(B, cb + k * 8);
+    if (k == 256) break;
+    if ((io.exp_val[k >> 5] >> (k & 31)) & 1) B = fq_mul(B, A);
+    A = fq_sqr(A);
+  }
+}
+// main columns: a16 b16 FqOutput(112) flags14   (reference src/fields/fq/exp.rs:128-178)
+__global__ void __launch_bounds__(128) k_fq_rows(const sbn_fq_exp_io* __restrict__ ios, const u32* __restrict__ chain, u64* __restrict__ cols, size_t N) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const size_t inst = r >> 9; const int rr = (int)(r & 511), k = rr >> 1;
+  u32 e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = ios[inst].exp_val[i];
+  u64 fl[14];
+  flags_row(e, rr, fl);
+  const u32* pa = chain + ((inst * 2) * 257 + k) * 8;
+  const u32* pb = chain + ((inst * 2 + 1) * 257 + k + (rr & 1)) * 8;
+  u32 a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a[i] = pa[i]; b[i] = pb[i]; }
+  const int op = fl[2] ? EXP_OP_SQUARE : (fl[4] ? EXP_OP_MUL : EXP_OP_NONE);
+  ColWriter w{cols + r, N};
+  fq_exp_row(a, b, op, w);
+#pragma unroll
+  for (int i = 0; i < 14; i++) w(144 + i, fl[i]);
+}
+static void generate_fq(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols, u64* h_results) {
+  const size_t n = air.num_io, N = air.num_rows;
+  DevBuf<sbn_fq_exp_io> buf; const sbn_fq_exp_io* d_ios = stage_ios(ctx, ios, on_device, n, buf);
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  DevBuf<u32> chain(ctx, n * 2 * 257 * 8);
+  { KScope ks(ctx, "fq_chain"); k_fq_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, chain, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "fq_rows"); k_fq_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, chain, d_cols, N); LAUNCH_CHECK(ctx); }
+  std::vector<u32> res(n * 8);
+  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 8, chain + ((i * 2 + 1) * 257 + 256) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  generate_exp_tail(ctx, air, d_cols, {144, 14, true, 512, 0, 9 * 16 - 1, false});
+  check_chain_error(ctx, err, "FqExpStark: internal error");
+  if (h_results) memcpy(h_results, res.data(), n * 32);
+}
+
+// ---------------- G2ExpStark (reference src/curves/g2/exp.rs) ----------------
+__global__ void __launch_bounds__(32) k_g2_chain(const sbn_g2_exp_io* __restrict__ ios, size_t num_io, G2Jac* __restrict__ jac /* [io][2][257] */, int* __restrict__ err) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= num_io) return;
+  const sbn_g2_exp_io& io = ios[i];
+  u32 w[16];
+  G2Jac A, B;
+  for (int t = 0; t < 4; t++) {
+    u64x4_to_words((const u64*)io.x + 4 * t, w); if (fq_geq_p(w)) *err = 2;
+    Fq v = fq_from_words(w); (t == 0 ? A.x.c0 : t == 1 ? A.x.c1 : t == 2 ? A.y.c0 : A.y.c1) = v;
+    u64x4_to_words((const u64*)io.offset + 4 * t, w); if (fq_geq_p(w)) *err = 2;
+    v = fq_from_words(w); (t == 0 ? B.x.c0 : t == 1 ? B.x.c1 : t == 2 ? B.y.c0 : B.y.c1) = v;
+  }
+  A.z = fq2_one(); B.z = fq2_one();
+  G2Jac* ja = jac + i * 2 * 257; G2Jac* jb = ja + 257;
+  ja[0] = A; jb[0] = B;
+  for (int k = 0; k < 256; k++) {
+    if ((io.exp_val[k >> 5] >> (k & 31)) & 1) B = g2_jac_add(A, B);
+    A = g2_jac_dbl(A);
+    ja[k + 1] = A; jb[k + 1] = B;
+  }
+}
+__global__ void __launch_bounds__(128) k_g2_affine(const G2Jac* __restrict__ jac, size_t npoints, u32* __restrict__ aff /* [point][32] */, int* __restrict__ err) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npoints) return;
+  G2Jac p = jac[i];
+  if (fq2_is_zero(p.z)) { *err = 1; return; }
+  Fq2 zi = fq2_inv(p.z), zi2 = fq2_sqr(zi);
+  Fq2 x = fq2_mul(p.x, zi2), y = fq2_mul(p.y, fq2_mul(zi2, zi));
+  u32 w[16];
+  fq2_to_words(x, w);
+#pragma unroll
+  for (int k = 0; k < 16; k++) aff[i * 32 + k] = w[k];
+  fq2_to_words(y, w);
+#pragma unroll
+  for (int k = 0; k < 16; k++) aff[i * 32 + 16 + k] = w[k];
+}
+// main columns: a(64) b(64) G2Output(640) flags(14)   (reference src/curves/g2/exp.rs:180-245)
+__global__ void __launch_bounds__(128) k_g2_rows(const sbn_g2_exp_io* __restrict__ ios, const u32* __restrict__ aff, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const size_t inst = r >> 9; const int rr = (int)(r & 511), k = rr >> 1;
+  u32 e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = ios[inst].exp_val[i];
+  u64 fl[14];
+  flags_row(e, rr, fl);
+  const u32* pa = aff + ((inst * 2) * 257 + k) * 32;
+  const u32* pb = aff + ((inst * 2 + 1) * 257 + k + (rr & 1)) * 32;
+  u32 ax[16], ay[16], bx[16], by[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { ax[i] = pa[i]; ay[i] = pa[16 + i]; bx[i] = pb[i]; by[i] = pb[16 + i]; }
+  const int op = fl[2] ? EXP_OP_SQUARE : (fl[4] ? EXP_OP_MUL : EXP_OP_NONE);   // a = is_double, filtered_bit = is_add
+  ColWriter w{cols + r, N};
+  if (!g2_row(ax, ay, bx, by, op, w)) *err = 1;
+#pragma unroll
+  for (int i = 0; i < 14; i++) w(768 + i, fl[i]);
+}
+static void generate_g2(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols, u64* h_results) {
+  const size_t n = air.num_io, N = air.num_rows;
+  DevBuf<sbn_g2_exp_io> buf; const sbn_g2_exp_io* d_ios = stage_ios(ctx, ios, on_device, n, buf);
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  const size_t npoints = n * 2 * 257;
+  DevBuf<G2Jac> jac(ctx, npoints);
+  DevBuf<u32> aff(ctx, npoints * 32);
+  { KScope ks(ctx, "g2_chain"); k_g2_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "g2_affine"); k_g2_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "g2_rows"); k_g2_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx); }
+  std::vector<u32> res(n * 32);
+  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 32, aff + ((i * 2 + 1) * 257 + 256) * 32, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  generate_exp_tail(ctx, air, d_cols, {768, 14, true, 512, 0, 48 * 16 - 6, false});
+  check_chain_error(ctx, err, "degenerate G2 input: the chain hit the point at infinity or two points with equal x (the reference panics here)");
+  if (h_results) memcpy(h_results, res.data(), n * 128);
+}
+
+// ---------------- Fq12ExpStark / Fq12ExpU64Stark (reference src/fields/fq12/exp.rs, src/fields/fq12_u64/exp_u64.rs) ----------------
+struct Fq12Io { u64 x[48], offset[48]; };   // common prefix of sbn_fq12_exp_io and sbn_fq12_exp_u64_io
+HD bool fq12_exp_bit(const void* io_base, size_t io_size, size_t inst, int k, bool u64_variant) {
+  const unsigned char* p = (const unsigned char*)io_base + inst * io_size + 768;
+  if (u64_variant) return (*(const u64*)p >> k) & 1;
+  return (((const u32*)p)[k >> 5] >> (k & 31)) & 1;
+}
+// One block per instance, 24 threads: threads 0..11 square A, threads 12..23 multiply B by A when the bit is set.
+// chain[inst][2][nbits+1][12][8]: canonical words of A[k] = x^(2^k) and B[k] = offset * prod_{j<k, bit_j} A[j].
+__global__ void __launch_bounds__(32) k_fq12_chain(const void* __restrict__ ios, size_t io_size, int nbits, bool u64_variant, u32* __restrict__ chain, int* __restrict__ err) {
+  __shared__ Fq sa[2][12], sb[2][12];
+  const size_t inst = blockIdx.x;
+  const int t = threadIdx.x, oi = t % 12, which = t / 12;
+  const Fq12Io* io = (const Fq12Io*)((const unsigned char*)ios + inst * io_size);
+  if (t < 24) {
+    u32 w[8];
+    u64x4_to_words((which ? io->offset : io->x) + 4 * oi, w);
+    if (fq_geq_p(w)) *err = 2;
+    (which ? sb : sa)[0][oi] = fq_from_words(w);
+  }
+  __syncthreads();
+  u32* ca = chain + inst * 2 * (size_t)(nbits + 1) * 96; u32* cb = ca + (size_t)(nbits + 1) * 96;
+  for (int k = 0; k <= nbits; k++) {
+    const int cur = k & 1, nxt = cur ^ 1;
+    if (t < 24) {
+      fq_to_words((which ? sb : sa)[cur][oi], (which ? cb : ca) + ((size_t)k * 12 + oi) * 8);
+      if (k < nbits) {
+        if (which == 0) sa[nxt][oi] = fq12_mul_coeff(sa[cur], sa[cur], oi);
+        else sb[nxt][oi] = fq12_exp_bit(ios, io_size, inst, k, u64_variant) ? fq12_mul_coeff(sb[cur], sa[cur], oi) : sb[cur][oi];
+      }
+    }
+    __syncthreads();
+  }
+}
+// main columns: a(192) b(192) Fq12Output(1344) flags   (reference src/fields/fq12/exp.rs:142-214).  Block = 32 rows x 12
+// coefficients; thread (row, oi) produces coefficient oi of the row's a, b and output block.
+__global__ void __launch_bounds__(384) k_fq12_rows(const void* __restrict__ ios, size_t io_size, int nbits, bool u64_variant, const u32* __restrict__ chain,
+                                                   u64* __restrict__ cols, size_t N) {
+  __shared__ unsigned short sx[32][192], sy[32][192];
+  const int lr = threadIdx.x & 31, oi = threadIdx.x >> 5;
+  const size_t r = blockIdx.x * (size_t)32 + lr;
+  const int rows_per_io = 2 * nbits;
+  const size_t inst = r / rows_per_io; const int rr = (int)(r % rows_per_io), k = rr >> 1;
+  const bool square = rr & 1;
+  const bool bit = fq12_exp_bit(ios, io_size, inst, k, u64_variant);
+  const int op = square ? EXP_OP_SQUARE : (bit ? EXP_OP_MUL : EXP_OP_NONE);
+  const u32* ca = chain + inst * 2 * (size_t)(nbits + 1) * 96; const u32* cb = ca + (size_t)(nbits + 1) * 96;
+  const u32* pa = ca + ((size_t)k * 12 + oi) * 8;                       // a = A[k]
+  const u32* pb = cb + ((size_t)(k + (square ? 1 : 0)) * 12 + oi) * 8;  // b = B[k] on even rows, B[k+1] on odd rows
+  u32 aw[8], bw[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { aw[i] = pa[i]; bw[i] = pb[i]; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    sx[lr][16 * oi + 2 * i] = aw[i] & 0xFFFF; sx[lr][16 * oi + 2 * i + 1] = aw[i] >> 16;
+    const u32 yv = square ? aw[i] : bw[i];
+    sy[lr][16 * oi + 2 * i] = yv & 0xFFFF; sy[lr][16 * oi + 2 * i + 1] = yv >> 16;
+  }
+  __syncthreads();
+  ColWriter w{cols + r, N};
+  write_limbs16(w, 16 * oi, aw); write_limbs16(w, 192 + 16 * oi, bw);
+  // output = a*a = A[k+1] on square rows, a*b = B[k+1] on multiplication rows
+  const u32* po = (square ? ca : cb) + ((size_t)(k + 1) * 12 + oi) * 8;
+  u32 ow[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) ow[i] = op == EXP_OP_NONE ? 0 : po[i];
+  fq12_row_coeff(sx[lr], sy[lr], ow, oi, op, w);
+  if (oi == 0) {
+    const int sf = 108 * 16;
+    const unsigned char* ep = (const unsigned char*)ios + inst * io_size + 768;
+    if (u64_variant) {
+      u64 fl[6]; flags_u64_row(*(const u64*)ep, rr, fl);
+      for (int i = 0; i < 6; i++) w(sf + i, fl[i]);
+    } else {
+      u32 e[8]; for (int i = 0; i < 8; i++) e[i] = ((const u32*)ep)[i];
+      u64 fl[14]; flags_row(e, rr, fl);
+      for (int i = 0; i < 14; i++) w(sf + i, fl[i]);
+    }
+  }
+}
+static void generate_fq12(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols, u64* h_results) {
+  const bool u64v = air.air_id == SBN_AIR_FQ12_EXP_U64;
+  const int nbits = u64v ? 64 : 256;
+  const size_t n = air.num_io, N = air.num_rows, io_size = air.io_size;
+  static_assert(sizeof(sbn_fq12_exp_io) == 1184 && sizeof(sbn_fq12_exp_u64_io) == 1160, "io layout");
+  DevBuf<unsigned char> buf; const void* d_ios = stage_ios<unsigned char>(ctx, ios, on_device, n * io_size, buf);
+  if (u64v) {   // exp_val must be a canonical field element (it is a public input: exp_u64.rs:106)
+    std::vector<unsigned char> h(n * io_size);
+    if (on_device) { CUDA_CHECK(cudaMemcpyAsync(h.data(), ios, h.size(), cudaMemcpyDeviceToHost, ctx->stream)); CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); }
+    else memcpy(h.data(), ios, h.size());
+    for (size_t i = 0; i < n; i++) { u64 e; memcpy(&e, h.data() + i * io_size + 768, 8); SBN_REQUIRE(e < GL_P, "Fq12ExpU64Stark: exp_val is not a canonical field element"); }
+  }
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  const size_t per_inst = (size_t)2 * (nbits + 1) * 96;
+  DevBuf<u32> chain(ctx, n * per_inst);
+  { KScope ks(ctx, "fq12_chain"); k_fq12_chain<<<(unsigned)n, 32, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "fq12_rows"); k_fq12_rows<<<(unsigned)(N / 32), 384, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, d_cols, N); LAUNCH_CHECK(ctx); }
+  std::vector<u32> res(n * 96);
+  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 96, chain + i * per_inst + (size_t)(nbits + 1) * 96 + (size_t)nbits * 96, 384, cudaMemcpyDeviceToHost, ctx->stream));
+  generate_exp_tail(ctx, air, d_cols, {108 * 16, u64v ? 6 : 14, !u64v, 2 * nbits, 24 * 16, 84 * 16 - 12, true});
+  check_chain_error(ctx, err, "Fq12ExpStark: internal error");
+  if (h_results) memcpy(h_results, res.data(), n * 384);
+}
+
 static void generate_modular(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols) {
   const size_t N = air.num_rows;
   DevBuf<u64> d_ios_buf; const u64* d_ios = (const u64*)ios;
@@ -300,7 +569,10 @@ void generate_trace(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool ios_
   switch (air.air_id) {
     case SBN_AIR_MODULAR: generate_modular(ctx, air, ios, ios_on_device, d_cols); break;
     case SBN_AIR_G1_EXP: generate_g1(ctx, air, ios, ios_on_device, d_cols, h_results); break;
-    default: throw SbnError(-3, "trace generation for this AIR is not implemented yet");
+    case SBN_AIR_FQ_EXP: generate_fq(ctx, air, ios, ios_on_device, d_cols, h_results); break;
+    case SBN_AIR_G2_EXP: generate_g2(ctx, air, ios, ios_on_device, d_cols, h_results); break;
+    case SBN_AIR_FQ12_EXP: case SBN_AIR_FQ12_EXP_U64: generate_fq12(ctx, air, ios, ios_on_device, d_cols, h_results); break;
+    default: throw SbnError(-3, "unknown AIR identifier");
   }
 }
 
@@ -318,6 +590,40 @@ void format_public_inputs(const AirDesc& air, const void* ios, u64* out) {
       }
       break;
     }
-    default: throw SbnError(-3, "public inputs for this AIR are not implemented yet");
+    case SBN_AIR_FQ_EXP: {  // reference src/fields/fq/exp.rs:103-111: x offset exp_val output, 8 u32 limbs each
+      const sbn_fq_exp_io* h = (const sbn_fq_exp_io*)ios;
+      for (size_t i = 0; i < air.num_io; i++) {
+        u64* o = out + 32 * i;
+        auto put = [&](const uint64_t* v, int slot) { for (int k = 0; k < 8; k++) o[8 * slot + k] = (v[k >> 1] >> (32 * (k & 1))) & 0xFFFFFFFFULL; };
+        put(h[i].x, 0); put(h[i].offset, 1);
+        for (int k = 0; k < 8; k++) o[16 + k] = h[i].exp_val[k];
+        put(h[i].output, 3);
+      }
+      break;
+    }
+    case SBN_AIR_G2_EXP: {  // reference src/curves/g2/exp.rs:139-156: x(4) offset(4) exp_val output(4), 8 u32 limbs each
+      const sbn_g2_exp_io* h = (const sbn_g2_exp_io*)ios;
+      for (size_t i = 0; i < air.num_io; i++) {
+        u64* o = out + 104 * i;
+        auto put = [&](const uint64_t* v, int slot) { for (int k = 0; k < 8; k++) o[8 * slot + k] = (v[k >> 1] >> (32 * (k & 1))) & 0xFFFFFFFFULL; };
+        for (int t = 0; t < 4; t++) { put(h[i].x + 4 * t, t); put(h[i].offset + 4 * t, 4 + t); put(h[i].output + 4 * t, 9 + t); }
+        for (int k = 0; k < 8; k++) o[64 + k] = h[i].exp_val[k];
+      }
+      break;
+    }
+    case SBN_AIR_FQ12_EXP: case SBN_AIR_FQ12_EXP_U64: {  // reference src/fields/fq12/exp.rs:107-124, fq12_u64/exp_u64.rs:102-122: u16 limbs
+      const bool u64v = air.air_id == SBN_AIR_FQ12_EXP_U64;
+      const size_t io_len = u64v ? 577 : 584;
+      for (size_t i = 0; i < air.num_io; i++) {
+        const unsigned char* rec = (const unsigned char*)ios + i * air.io_size;
+        u64* o = out + io_len * i;
+        auto put12 = [&](const unsigned char* src, u64* dst) { for (int k = 0; k < 192; k++) { uint16_t v; memcpy(&v, src + 2 * k, 2); dst[k] = v; } };   // little-endian host
+        put12(rec, o); put12(rec + 384, o + 192);
+        if (u64v) { u64 e; memcpy(&e, rec + 768, 8); SBN_REQUIRE(e < GL_P, "exp_val is not a canonical field element"); o[384] = e; put12(rec + 776, o + 385); }
+        else { for (int k = 0; k < 8; k++) { uint32_t e; memcpy(&e, rec + 768 + 4 * k, 4); o[384 + k] = e; } put12(rec + 800, o + 392); }
+      }
+      break;
+    }
+    default: throw SbnError(-3, "unknown AIR identifier");
   }
 }

@@ -103,3 +103,187 @@ def g1_mul(p, e):
         p = g1_add(p, p)
         e >>= 1
     return r
+
+
+def fill_outputs(ios, results, io_size, out_off):
+    """Generic form of fill_g1_outputs: copy each io's chain result into the record's output field."""
+    b = bytearray(ios)
+    n = len(b) // io_size
+    w = (io_size - out_off) // 8
+    for i in range(n):
+        b[i * io_size + out_off:(i + 1) * io_size] = bytes(results[i][:w].tobytes())
+    return bytes(b)
+
+
+# ---------------- Fq (reference src/fields/fq/exp.rs:88-93 `FqExpIONative`) ----------------
+FQ_IO_SIZE = 128
+
+
+def fq_exp_ios(num_io, seed=0x5EED0000):
+    """x, offset uniform non-zero residues; exp_val a full 256-bit value (reference fq/exp.rs:575-590)."""
+    rng = SplitMix64(seed)
+    out = bytearray()
+    for _ in range(num_io):
+        out += _le32(1 + rng.below(BN254_P - 1)) + _le32(1 + rng.below(BN254_P - 1))
+        out += struct.pack("<8I", *[rng.next() & 0xFFFFFFFF for _ in range(8)])
+        out += bytes(32)
+    return bytes(out)
+
+
+# ---------------- Fq2 / G2 (reference src/curves/g2/exp.rs:90-95 `G2ExpIONative`) ----------------
+def fq2_add(a, b):
+    return (a[0] + b[0]) % BN254_P, (a[1] + b[1]) % BN254_P
+
+
+def fq2_sub(a, b):
+    return (a[0] - b[0]) % BN254_P, (a[1] - b[1]) % BN254_P
+
+
+def fq2_mul(a, b):
+    return (a[0] * b[0] - a[1] * b[1]) % BN254_P, (a[0] * b[1] + a[1] * b[0]) % BN254_P
+
+
+def fq2_inv(a):
+    n = pow(a[0] * a[0] + a[1] * a[1], -1, BN254_P)
+    return a[0] * n % BN254_P, -a[1] * n % BN254_P
+
+
+def _fq_sqrt(a):
+    r = pow(a, (BN254_P + 1) // 4, BN254_P)
+    return r if r * r % BN254_P == a % BN254_P else None
+
+
+def fq2_sqrt(a):
+    if a[1] == 0:
+        r = _fq_sqrt(a[0])
+        if r is not None:
+            return r, 0
+        r = _fq_sqrt(-a[0] % BN254_P)   # sqrt(-c) * u
+        return (0, r) if r is not None else None
+    s = _fq_sqrt((a[0] * a[0] + a[1] * a[1]) % BN254_P)
+    if s is None:
+        return None
+    inv2 = pow(2, -1, BN254_P)
+    for t in ((a[0] + s) * inv2 % BN254_P, (a[0] - s) * inv2 % BN254_P):
+        x0 = _fq_sqrt(t)
+        if x0:
+            x1 = a[1] * pow(2 * x0, -1, BN254_P) % BN254_P
+            if fq2_mul((x0, x1), (x0, x1)) == (a[0] % BN254_P, a[1] % BN254_P):
+                return x0, x1
+    return None
+
+
+G2_B = fq2_mul((3, 0), fq2_inv((9, 1)))   # twist y^2 = x^3 + 3/(9+u)
+
+
+def random_g2(rng):
+    """Random affine point on the twist (need not be in the r-torsion: the AIR only needs curve points)."""
+    while True:
+        x = (rng.below(BN254_P), rng.below(BN254_P))
+        rhs = fq2_add(fq2_mul(fq2_mul(x, x), x), G2_B)
+        y = fq2_sqrt(rhs)
+        if y is not None and y != (0, 0):
+            if rng.next() & 1:
+                y = (-y[0] % BN254_P, -y[1] % BN254_P)
+            return x, y
+
+
+def g2_add(p, q):
+    if p is None:
+        return q
+    if q is None:
+        return p
+    if p[0] == q[0]:
+        if fq2_add(p[1], q[1]) == (0, 0):
+            return None
+        lam = fq2_mul(fq2_mul((3, 0), fq2_mul(p[0], p[0])), fq2_inv(fq2_mul((2, 0), p[1])))
+    else:
+        lam = fq2_mul(fq2_sub(q[1], p[1]), fq2_inv(fq2_sub(q[0], p[0])))
+    x = fq2_sub(fq2_sub(fq2_mul(lam, lam), p[0]), q[0])
+    return x, fq2_sub(fq2_mul(lam, fq2_sub(p[0], x)), p[1])
+
+
+def g2_mul(p, e):
+    r = None
+    while e:
+        if e & 1:
+            r = g2_add(r, p)
+        p = g2_add(p, p)
+        e >>= 1
+    return r
+
+
+G2_IO_SIZE = 416
+
+
+def _g2_bytes(p):
+    return _le32(p[0][0]) + _le32(p[0][1]) + _le32(p[1][0]) + _le32(p[1][1])
+
+
+def g2_exp_ios(num_io, seed=0x5EED0002):
+    """G2ExpIONative records: x, offset as (x.c0, x.c1, y.c0, y.c1), exp_val[8 x u32], output left zero."""
+    rng = SplitMix64(seed)
+    out = bytearray()
+    for _ in range(num_io):
+        out += _g2_bytes(random_g2(rng)) + _g2_bytes(random_g2(rng))
+        out += struct.pack("<8I", *[rng.next() & 0xFFFFFFFF for _ in range(8)])
+        out += bytes(128)
+    return bytes(out)
+
+
+# ---------------- Fq12 in the flat MyFq12 basis (reference src/fields/fq12/exp.rs:90-95) ----------------
+def fq12_mul(a, b):
+    """sum_{i<6} (c[i] + c[i+6] u) w^i with u^2 = -1, w^6 = 9 + u (reference fq12/mul.rs:24-87)."""
+    re, im = [0] * 11, [0] * 11
+    for i in range(6):
+        for j in range(6):
+            re[i + j] += a[i] * b[j] - a[i + 6] * b[j + 6]
+            im[i + j] += a[i] * b[j + 6] + a[i + 6] * b[j]
+    out = [0] * 12
+    for i in range(6):
+        if i < 5:
+            out[i] = (re[i] + 9 * re[i + 6] - im[i + 6]) % BN254_P
+            out[i + 6] = (im[i] + re[i + 6] + 9 * im[i + 6]) % BN254_P
+        else:
+            out[i], out[i + 6] = re[i] % BN254_P, im[i] % BN254_P
+    return out
+
+
+def fq12_pow_mul(x, e, offset):
+    acc = list(offset)
+    while e:
+        if e & 1:
+            acc = fq12_mul(acc, x)
+        x = fq12_mul(x, x)
+        e >>= 1
+    return acc
+
+
+FQ12_IO_SIZE = 1184
+FQ12_U64_IO_SIZE = 1160
+
+
+def fq12_exp_ios(num_io, seed=0x5EED0003):
+    """x, offset uniform in Fq12 (12 residues each); exponent uniform below r (`Fr::rand`, reference fq12/exp.rs:649)."""
+    rng = SplitMix64(seed)
+    out = bytearray()
+    for _ in range(num_io):
+        for _ in range(24):
+            out += _le32(rng.below(BN254_P))
+        out += _le32(rng.below(BN254_R))
+        out += bytes(384)
+    return bytes(out)
+
+
+def fq12_exp_u64_ios(num_io, seed=0x5EED0004):
+    rng = SplitMix64(seed)
+    out = bytearray()
+    for _ in range(num_io):
+        for _ in range(24):
+            out += _le32(rng.below(BN254_P))
+        out += struct.pack("<Q", rng.below(P_GOLDILOCKS))
+        out += bytes(384)
+    return bytes(out)
+
+
+P_GOLDILOCKS = 2**64 - 2**32 + 1

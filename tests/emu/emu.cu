@@ -32,6 +32,19 @@ int emu_eval_air(int air_id, size_t num_io, const u64* lv, const u64* nv, const 
         case SEG_PERIODIC_PULSE: eval_periodic_pulse(q, s.p0, s.p1, s.p2, s.p3); break;
         case SEG_PULSE: eval_pulse(q, s.p0, s.p1, s.p2); break;
         case SEG_U16_RANGE_CHECK: eval_u16_range_check(q, s.p0, s.p1); break;
+        case SEG_FQ_CORE: eval_exp_core_u32<1>(q, s.p0, s.p1, s.p2); break;
+        case SEG_G2_CORE: eval_exp_core_u32<4>(q, s.p0, s.p1, s.p2); break;
+        case SEG_FQ_MUL: eval_fq_mul(q, q.lv(s.p0), s.p1 != 0); break;
+        case SEG_G2_ADD: eval_g2_add(q, q.lv(s.p1), s.p0); break;
+        case SEG_G2_DOUBLE: eval_g2_double(q, q.lv(s.p1), s.p0); break;
+        case SEG_FQ12_CORE: eval_fq12_exp_core(q, s.p0, s.p1, s.p2 != 0); break;
+        case SEG_FQ12_MUL: {   // k_fq12_products' per-thread body
+          std::vector<u64> prod(12 * 31);
+          for (int oi = 0; oi < 12; oi++) { F acc[31]; fq12_product_acc(q, 0, s.p1 ? 0 : 192, oi, acc); for (int k = 0; k < 31; k++) prod[oi * 31 + k] = acc[k].v; }
+          eval_fq12_mul(q, q.lv(s.p0), prod.data(), 1);
+          break;
+        }
+        case SEG_FLAGS_U64: eval_flags_u64(q, s.p0); break;
         default: return -1;
       }
       for (int c = 0; c < 2; c++) acc[c] = gl_add(gl_mul(acc[c], gl_pow(alphas[c], s.num_constraints)), q.acc[c].v);
@@ -65,4 +78,50 @@ void emu_g1_chain(const u64* x_x, const u64* x_y, const u64* o_x, const u64* o_y
     store(A, affA + (k + 1) * 16); store(B, affB + (k + 1) * 16);
   }
 }
+// FqExp main columns a,b,output (144) of one row
+void emu_fq_exp_row(const u32* a, const u32* b, int op, u64* row) { RowWriter w{row}; fq_exp_row(a, b, op, w); }
+// G2 main columns a,b,output (768) of one row; returns 0 if the slope denominator vanished
+int emu_g2_row(const u32* ax, const u32* ay, const u32* bx, const u32* by, int op, u64* row) { RowWriter w{row}; return g2_row(ax, ay, bx, by, op, w) ? 1 : 0; }
+// Jacobian G2 chain of one instance -> affine canonical words (32 per point: x.c0 x.c1 y.c0 y.c1) of A[k], B[k], k = 0..nsteps
+void emu_g2_chain(const u64* x /*16*/, const u64* off /*16*/, const u32* e, int nsteps, u32* affA, u32* affB) {
+  u32 w[16]; G2Jac A, B;
+  auto load = [&](const u64* p, G2Jac& P) {
+    for (int t = 0; t < 4; t++) u64x4_to_words(p + 4 * t, w + 0), (t == 0 ? P.x.c0 : t == 1 ? P.x.c1 : t == 2 ? P.y.c0 : P.y.c1) = fq_from_words(w);
+    P.z = fq2_one();
+  };
+  load(x, A); load(off, B);
+  auto store = [&](const G2Jac& p, u32* out) {
+    Fq2 zi = fq2_inv(p.z), zi2 = fq2_sqr(zi);
+    Fq2 xx = fq2_mul(p.x, zi2), yy = fq2_mul(p.y, fq2_mul(zi2, zi));
+    fq2_to_words(xx, out); fq2_to_words(yy, out + 16);
+  };
+  store(A, affA); store(B, affB);
+  for (int k = 0; k < nsteps; k++) {
+    if ((e[k >> 5] >> (k & 31)) & 1) B = g2_jac_add(A, B);
+    A = g2_jac_dbl(A);
+    store(A, affA + (k + 1) * 32); store(B, affB + (k + 1) * 32);
+  }
+}
+// Fq12 product in the flat basis through the chain's per-coefficient routine: canonical words in and out (12 x 8)
+void emu_fq12_mul(const u32* x, const u32* y, u32* out) {
+  Fq xm[12], ym[12];
+  for (int i = 0; i < 12; i++) { xm[i] = fq_from_words(x + 8 * i); ym[i] = fq_from_words(y + 8 * i); }
+  for (int oi = 0; oi < 12; oi++) fq_to_words(fq12_mul_coeff(xm, ym, oi), out + 8 * oi);
+}
+// Fq12 main columns a,b,output (1728) of one row, written the way k_fq12_rows does (one coefficient at a time)
+void emu_fq12_row(const u32* a, const u32* b, const u32* out_words, int op, u64* row) {
+  RowWriter w{row};
+  unsigned short sx[192], sy[192];
+  const bool square = op == EXP_OP_SQUARE;
+  for (int oi = 0; oi < 12; oi++) for (int i = 0; i < 8; i++) {
+    sx[16 * oi + 2 * i] = a[8 * oi + i] & 0xFFFF; sx[16 * oi + 2 * i + 1] = a[8 * oi + i] >> 16;
+    u32 yv = square ? a[8 * oi + i] : b[8 * oi + i];
+    sy[16 * oi + 2 * i] = yv & 0xFFFF; sy[16 * oi + 2 * i + 1] = yv >> 16;
+  }
+  for (int oi = 0; oi < 12; oi++) {
+    write_limbs16(w, 16 * oi, a + 8 * oi); write_limbs16(w, 192 + 16 * oi, b + 8 * oi);
+    fq12_row_coeff(sx, sy, out_words + 8 * oi, oi, op, w);
+  }
+}
+void emu_flags_u64_row(u64 e, int r, u64* out) { flags_u64_row(e, r, out); }
 }

@@ -57,6 +57,28 @@ def main():
     else:
         old = json.load(open(os.path.join(HERE, "golden.json")))
         out["g1_128"] = old["g1_128"]
+    # FqExpStark n=128, G2ExpStark n=128, Fq12ExpStark n=16, Fq12ExpU64Stark n=16 (BASELINE.json configs 3-4 and SURVEY §8 f1)
+    old = json.load(open(os.path.join(HERE, "golden.json"))) if os.path.exists(os.path.join(HERE, "golden.json")) else {}
+    more = [("fq_128", orc.AIR_FQ_EXP, 128, syn.fq_exp_ios, syn.FQ_IO_SIZE, 96), ("g2_128", orc.AIR_G2_EXP, 128, syn.g2_exp_ios, syn.G2_IO_SIZE, 288),
+            ("fq12_16", orc.AIR_FQ12_EXP, 16, syn.fq12_exp_ios, syn.FQ12_IO_SIZE, 800), ("fq12u64_16", orc.AIR_FQ12_EXP_U64, 16, syn.fq12_exp_u64_ios, syn.FQ12_U64_IO_SIZE, 776)]
+    only = [a.split("=")[1] for a in sys.argv if a.startswith("--only=")]
+    for name, air_id, n, gen, io_size, out_off in more:
+        if (only and name not in only) or ("--skip-new" in sys.argv):
+            if name in old:
+                out[name] = old[name]
+            continue
+        ios = gen(n)
+        air = orc.Air(air_id, n)
+        trace, res = air.generate_trace(ios)
+        ios = syn.fill_outputs(ios, res, io_size, out_off)
+        pi = air.generate_public_inputs(ios)
+        proof = air.prove(trace, pi)
+        assert air.verify(proof)[0]
+        out[name] = {"ios_sha256": sha(ios), "trace_sha256": sha(trace.tobytes()), "results_sha256": sha(res.tobytes()), "pi_sha256": sha(pi.tobytes()),
+                     "proof_sha256": sha(proof), "proof_len": len(proof),
+                     "trace_cap0": ["%016x" % int.from_bytes(proof[4 + 8 * i:12 + 8 * i], "little") for i in range(4)]}
+        print(name, out[name], flush=True)
+        del trace, proof
     json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 

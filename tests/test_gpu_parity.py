@@ -167,6 +167,94 @@ def test_g1_trace_and_proof_match_golden(ctx, sbn, orc, golden):
     assert not air.verify(bytes(t))[0]
 
 
+def _semantic_fq12(syn, ios, res, io_size, u64v):
+    b0 = ios[:io_size]
+    c12 = lambda o: [int.from_bytes(b0[o + 32 * i:o + 32 * i + 32], "little") for i in range(12)]
+    e = int.from_bytes(b0[768:776 if u64v else 800], "little")
+    return [int.from_bytes(res[0][4 * i:4 * i + 4].tobytes(), "little") for i in range(12)] == syn.fq12_pow_mul(c12(0), e, c12(384))
+
+
+@pytest.mark.parametrize("name,cls_name,air_id,n,gen,io_size_name", [
+    ("fq_128", "FqExpStark", 1, 128, "fq_exp_ios", "FQ_IO_SIZE"),
+    ("g2_128", "G2ExpStark", 3, 128, "g2_exp_ios", "G2_IO_SIZE"),
+    ("fq12_16", "Fq12ExpStark", 4, 16, "fq12_exp_ios", "FQ12_IO_SIZE"),
+    ("fq12u64_16", "Fq12ExpU64Stark", 5, 16, "fq12_exp_u64_ios", "FQ12_U64_IO_SIZE"),
+])
+def test_exp_airs_trace_and_proof_match_golden(ctx, sbn, orc, golden, name, cls_name, air_id, n, gen, io_size_name):
+    """FqExp / G2Exp / Fq12Exp / Fq12ExpU64 at the reference's test shapes (src/curves/g2/exp.rs:836-894,
+    src/fields/fq12/exp.rs:638-696, ...): GPU trace and proof against the committed digests of the oracle's output,
+    then the oracle's verifier, then tamper rejection."""
+    g = golden[name]
+    syn = sbn.synthetic
+    ios = getattr(syn, gen)(n)
+    stark = getattr(sbn, cls_name)(n, ctx)
+    trace = stark.generate_trace(ios)
+    res = trace.results()
+    assert hashlib.sha256(res.tobytes()).hexdigest() == g["results_sha256"]
+    cols = trace.download()
+    if hashlib.sha256(cols.tobytes()).hexdigest() != g["trace_sha256"]:
+        want_cols, _ = orc.Air(air_id, n).generate_trace(ios)
+        bad = np.nonzero((cols != want_cols).any(axis=1))[0]
+        pytest.fail("%s trace columns differ from the oracle: %s" % (name, bad[:20]))
+    del cols
+    ios = syn.fill_outputs(ios, res, stark.io_size, stark.io_size - 8 * stark.result_words)
+    assert hashlib.sha256(ios).hexdigest() == g["ios_sha256"]
+    pi = stark.generate_public_inputs(ios)
+    assert hashlib.sha256(pi.tobytes()).hexdigest() == g["pi_sha256"]
+    proof = sbn.prove(stark, stark.config(), trace, pi)
+    pb = proof.to_bytes()
+    air = orc.Air(air_id, n)
+    ok, why = air.verify(pb)
+    assert ok, why
+    assert len(pb) == g["proof_len"]
+    assert ["%016x" % int.from_bytes(pb[4 + 8 * i:12 + 8 * i], "little") for i in range(4)] == g["trace_cap0"]
+    assert hashlib.sha256(pb).hexdigest() == g["proof_sha256"]
+    t = bytearray(pb); t[len(t) // 3] ^= 4
+    assert not air.verify(bytes(t))[0]
+    t = bytearray(pb); t[-8] ^= 1     # last public input
+    assert not air.verify(bytes(t))[0]
+
+
+@pytest.mark.parametrize("cls_name,air_id,n,gen", [("Fq12ExpStark", 4, 1, "fq12_exp_ios"), ("Fq12ExpU64Stark", 5, 2, "fq12_exp_u64_ios"), ("Fq12ExpStark", 4, 2, "fq12_exp_ios")])
+def test_fq12_small_proofs_match_oracle_bytes(ctx, sbn, orc, cls_name, air_id, n, gen, monkeypatch):
+    """Smallest Fq12 shapes (512 / 256 / 1024 rows): the oracle prover runs in seconds, so compare stage by stage and byte for byte."""
+    monkeypatch.setenv("SBN_DEBUG_INTERMEDIATES", "1")
+    syn = sbn.synthetic
+    ios = getattr(syn, gen)(n, seed=4242 + n)
+    stark = getattr(sbn, cls_name)(n, ctx)
+    trace = stark.generate_trace(ios)
+    res = trace.results()
+    assert _semantic_fq12(syn, ios, res, stark.io_size, air_id == 5)
+    air = orc.Air(air_id, n)
+    otrace, ores = air.generate_trace(ios)
+    got = trace.download()
+    bad = np.nonzero((got != otrace).any(axis=1))[0]
+    assert len(bad) == 0, "columns differ: %s" % bad[:10]
+    assert (res == ores).all()
+    ios = syn.fill_outputs(ios, res, stark.io_size, stark.io_size - 8 * stark.result_words)
+    pi = stark.generate_public_inputs(ios)
+    proof = sbn.prove(stark, stark.config(), trace, pi)
+    oproof = air.prove(otrace, pi)
+    N = stark.num_rows
+    assert (proof.debug("z_polys").reshape(-1, N) == orc.dbg_z_polys(N)).all(), "Z polynomials differ"
+    assert (proof.debug("quotient_chunks").reshape(-1, N) == orc.dbg_quotient_chunks(N)).all(), "quotient chunks differ"
+    assert proof.to_bytes() == oproof
+    assert air.verify(proof.to_bytes()) == (True, "")
+
+
+def test_g2_semantic_result(ctx, sbn):
+    syn = sbn.synthetic
+    n = 128
+    ios = syn.g2_exp_ios(n, seed=99)
+    res = sbn.G2ExpStark(n, ctx).generate_trace(ios).results()
+    for k in (0, 77, 127):
+        b = ios[k * syn.G2_IO_SIZE:(k + 1) * syn.G2_IO_SIZE]
+        I = lambda o: int.from_bytes(b[o:o + 32], "little")
+        x = ((I(0), I(32)), (I(64), I(96))); off = ((I(128), I(160)), (I(192), I(224))); e = I(256)
+        w = lambda i: int.from_bytes(res[k][4 * i:4 * i + 4].tobytes(), "little")
+        assert ((w(0), w(1)), (w(2), w(3))) == syn.g2_add(syn.g2_mul(x, e), off)
+
+
 def test_error_paths(ctx, sbn):
     stark = sbn.ModularStark(512, ctx)
     q = sbn.synthetic.BN254_P

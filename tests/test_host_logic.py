@@ -58,7 +58,7 @@ def test_public_inputs_match_oracle(sbn, orc):
     assert (sbn.G1ExpStark(n).generate_public_inputs(ios) == orc.Air(orc.AIR_G1_EXP, n).generate_public_inputs(ios)).all()
 
 
-@pytest.mark.parametrize("air_id,num_io", [(0, 512), (2, 128)])
+@pytest.mark.parametrize("air_id,num_io", [(0, 512), (2, 128), (1, 128), (3, 128), (4, 1), (4, 4), (5, 2)])
 def test_constraint_segments_match_oracle_consumer(emu, orc, air_id, num_io):
     air = orc.Air(air_id, num_io)
     rng = random.Random(11 + air_id)
@@ -168,3 +168,130 @@ def test_product_poseidon_host_path_kat(emu):
     st = np.zeros(12, dtype=np.uint64)
     emu.emu_poseidon(vp(st))
     assert int(st[0]) == 0x3c18a9786cb0b359 and int(st[11]) == 0x1792b1c4342109d7
+
+
+def _w8(v):
+    return np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+
+
+def _ops_from_flags(trace, sf, r, u64_variant=False):
+    """0 none, 1 mul/add (filtered_bit), 2 square/double (a) -- EXP_OP_* of witness.cuh."""
+    a_col, fbit_col = (sf + 1, sf + 3) if u64_variant else (sf + 2, sf + 4)
+    return 2 if trace[a_col, r] == 1 else (1 if trace[fbit_col, r] == 1 else 0)
+
+
+def test_fq_exp_rows_match_oracle(emu, orc, sbn):
+    n = 128
+    ios = sbn.synthetic.fq_exp_ios(n, seed=5)
+    trace, res = orc.Air(orc.AIR_FQ_EXP, n).generate_trace(ios)
+    limbs = lambda r, c0: np.array([int(trace[c0 + 2 * i, r]) | (int(trace[c0 + 2 * i + 1, r]) << 16) for i in range(8)], dtype=np.uint32)
+    for r in list(range(0, 40)) + [510, 511, 512, 513, 65535]:
+        row = np.zeros(144, dtype=np.uint64)
+        emu.emu_fq_exp_row(vp(limbs(r, 0)), vp(limbs(r, 16)), C.c_int(_ops_from_flags(trace, 144, r)), vp(row))
+        assert (row == trace[:144, r]).all(), r
+    # semantic: chain result = offset * x^e (reference fq/exp.rs:241-244)
+    b = ios[:128]
+    I = lambda o: int.from_bytes(b[o:o + 32], "little")
+    q = sbn.synthetic.BN254_P
+    assert int.from_bytes(res[0][:4].tobytes(), "little") == I(32) * pow(I(0), I(64), q) % q
+
+
+def test_g2_chain_and_rows_match_bigint_arithmetic(emu, sbn):
+    syn = sbn.synthetic
+    ios = syn.g2_exp_ios(1, seed=78)
+    b = ios[:syn.G2_IO_SIZE]
+    I = lambda o: int.from_bytes(b[o:o + 32], "little")
+    x = ((I(0), I(32)), (I(64), I(96))); off = ((I(128), I(160)), (I(192), I(224))); e = I(256) & ((1 << 40) - 1)
+    A = np.zeros((41, 32), dtype=np.uint32); B = np.zeros((41, 32), dtype=np.uint32)
+    ew = np.array([(e >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+    emu.emu_g2_chain(vp(np.frombuffer(b[0:128], dtype=np.uint64).copy()), vp(np.frombuffer(b[128:256], dtype=np.uint64).copy()), vp(ew), C.c_int(40), vp(A), vp(B))
+    words = lambda w: sum(int(v) << (32 * i) for i, v in enumerate(w))
+    pt = lambda w: ((words(w[0:8]), words(w[8:16])), (words(w[16:24]), words(w[24:32])))
+    assert pt(B[40]) == syn.g2_add(syn.g2_mul(x, e), off)
+    assert pt(A[5]) == syn.g2_mul(x, 32)
+    w16 = lambda c: np.concatenate([_w8(c[0]), _w8(c[1])])
+    for op, p1, p2 in ((1, x, off), (2, x, x)):
+        row = np.zeros(768, dtype=np.uint64)
+        assert emu.emu_g2_row(vp(w16(p1[0])), vp(w16(p1[1])), vp(w16(p2[0])), vp(w16(p2[1])), C.c_int(op), vp(row)) == 1
+        lim = lambda c0: sum(int(row[c0 + i]) << (16 * i) for i in range(16))
+        got = ((lim(128 + 32), lim(128 + 48)), (lim(128 + 64), lim(128 + 80)))
+        assert got == syn.g2_add(p1, p2)
+        assert int(row[:128 + 634].max()) < 65536
+    neg = (x[0], (-x[1][0] % syn.BN254_P, -x[1][1] % syn.BN254_P))
+    row = np.zeros(768, dtype=np.uint64)
+    assert emu.emu_g2_row(vp(w16(x[0])), vp(w16(x[1])), vp(w16(neg[0])), vp(w16(neg[1])), C.c_int(1), vp(row)) == 0
+
+
+@pytest.mark.parametrize("air_id,num_io,rows", [(4, 1, 512), (5, 2, 128)])
+def test_fq12_rows_match_oracle(emu, orc, sbn, air_id, num_io, rows):
+    syn = sbn.synthetic
+    u64v = air_id == 5
+    ios = syn.fq12_exp_u64_ios(num_io, seed=9) if u64v else syn.fq12_exp_ios(num_io, seed=9)
+    air = orc.Air(air_id, num_io)
+    trace, res = air.generate_trace(ios)
+    sf = 108 * 16
+    words = lambda r, c0: np.array([int(trace[c0 + 2 * i, r]) | (int(trace[c0 + 2 * i + 1, r]) << 16) for i in range(96)], dtype=np.uint32)
+    for r in list(range(0, 12)) + [rows - 2, rows - 1, rows, rows + 1]:
+        if r >= trace.shape[1]:
+            continue
+        op = _ops_from_flags(trace, sf, r, u64v)
+        a, b, out = words(r, 0), words(r, 192), words(r, 384)
+        row = np.zeros(1728, dtype=np.uint64)
+        emu.emu_fq12_row(vp(a), vp(b), vp(out), C.c_int(op), vp(row))
+        assert (row == trace[:1728, r]).all(), (r, np.nonzero(row != trace[:1728, r])[0][:8])
+        if op:
+            got = np.zeros(96, dtype=np.uint32)
+            emu.emu_fq12_mul(vp(a), vp(a if op == 2 else b), vp(got))
+            assert (got == out).all(), r
+        # flag columns
+        if u64v:
+            e = int.from_bytes(ios[(r // 128) * syn.FQ12_U64_IO_SIZE + 768:(r // 128) * syn.FQ12_U64_IO_SIZE + 776], "little")
+            fl = np.zeros(6, dtype=np.uint64)
+            emu.emu_flags_u64_row(C.c_uint64(e), C.c_int(r % 128), vp(fl))
+            assert (fl == trace[sf:sf + 6, r]).all(), r
+    # semantic check of the chain result (reference fq12/exp.rs:277-279)
+    size = syn.FQ12_U64_IO_SIZE if u64v else syn.FQ12_IO_SIZE
+    b0 = ios[:size]
+    c12 = lambda o: [int.from_bytes(b0[o + 32 * i:o + 32 * i + 32], "little") for i in range(12)]
+    e = int.from_bytes(b0[768:776 if u64v else 800], "little")
+    want = syn.fq12_pow_mul(c12(0), e, c12(384))
+    assert [int.from_bytes(res[0][4 * i:4 * i + 4].tobytes(), "little") for i in range(12)] == want
+
+
+def test_flags_u64_closed_form_matches_sequential_generation(emu):
+    rng = random.Random(17)
+    for e in (0, 1, (1 << 64) - (1 << 32), rng.getrandbits(64) % P, 1 << 63):
+        bit = e & 1; val = e >> 1
+        rows = [[0, 0, 1, bit, bit, val]]
+        for cur in range(127):
+            lv = rows[-1]
+            nv = [1 if cur == 126 else 0, 1 - lv[1], 1 - lv[2], 0, 0, 0]
+            if lv[1] == 1:
+                nv[4] = lv[5] & 1; nv[5] = lv[5] >> 1
+            else:
+                nv[4] = lv[4]; nv[5] = lv[5]
+            nv[3] = nv[4] * nv[2]
+            rows.append(nv)
+        for r in range(128):
+            out = np.zeros(6, dtype=np.uint64)
+            emu.emu_flags_u64_row(C.c_uint64(e), C.c_int(r), vp(out))
+            assert [int(x) for x in out] == rows[r], (e, r)
+
+
+def test_air_info_new_airs(sbn, orc):
+    for cls, air_id, n in ((sbn.FqExpStark, 1, 128), (sbn.G2ExpStark, 3, 128), (sbn.Fq12ExpStark, 4, 16), (sbn.Fq12ExpU64Stark, 5, 16)):
+        st = cls(n)
+        o = orc.Air(air_id, n)
+        assert (st.num_columns, st.num_public_inputs, st.num_rows, st.num_permutation_pairs, st.io_size, st.result_words) == \
+               (o.num_columns, o.num_public_inputs, o.num_rows, o.num_pairs, o.io_size, o.result_words)
+    assert sbn.G2ExpStark(128).num_columns == 2822 and sbn.Fq12ExpStark(16).num_columns == 9802 and sbn.FqExpStark(128).num_columns == 960
+
+
+def test_public_inputs_new_airs_match_oracle(sbn, orc):
+    syn = sbn.synthetic
+    for cls, air_id, n, ios in ((sbn.FqExpStark, 1, 128, syn.fq_exp_ios(128)), (sbn.G2ExpStark, 3, 128, syn.g2_exp_ios(128)),
+                                (sbn.Fq12ExpStark, 4, 2, syn.fq12_exp_ios(2)), (sbn.Fq12ExpU64Stark, 5, 2, syn.fq12_exp_u64_ios(2))):
+        st = cls(n)
+        res = (np.arange(n * st.result_words, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(n, st.result_words)
+        ios2 = syn.fill_outputs(ios, res, st.io_size, st.io_size - 8 * st.result_words)
+        assert (st.generate_public_inputs(ios2) == orc.Air(air_id, n).generate_public_inputs(ios2)).all(), air_id
