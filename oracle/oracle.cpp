@@ -43,6 +43,7 @@ static Fq12Words mk12(const u64* p) { Fq12Words w; for (int i = 0; i < 12; i++) 
 extern "C" {
 const char* orc_last_error() { return g_err.c_str(); }
 void orc_set_field_params(u64 gen, u64 pow2) { g_field.mult_generator = gen; g_field.pow2_generator = pow2; }
+void orc_poseidon_fast(u64* st) { GF s[12]; for (int i = 0; i < 12; i++) s[i] = GF(st[i]); poseidon_fast(s); for (int i = 0; i < 12; i++) st[i] = s[i].v; }
 void orc_poseidon(u64* st) { GF s[12]; for (int i = 0; i < 12; i++) s[i] = GF(st[i]); poseidon(s); for (int i = 0; i < 12; i++) st[i] = s[i].v; }
 void orc_hash_or_noop(const u64* in, size_t n, u64* out4) { std::vector<GF> v(n); for (size_t i = 0; i < n; i++) v[i] = GF(in[i]); Hash4 h = hash_or_noop(v.data(), n); for (int i = 0; i < 4; i++) out4[i] = h.e[i].v; }
 void orc_two_to_one(const u64* l, const u64* r, u64* out4) { Hash4 a, b; for (int i = 0; i < 4; i++) { a.e[i] = GF(l[i]); b.e[i] = GF(r[i]); } Hash4 h = two_to_one(a, b); for (int i = 0; i < 4; i++) out4[i] = h.e[i].v; }

@@ -228,7 +228,7 @@ static inline GF fri_proof_of_work(Challenger& ch, const StarkConfig& cfg) {
       if ((u64)c > best) continue;
       GF st[12]; for (int i = 0; i < 12; i++) st[i] = st0[i];
       st[pos] = GF((u64)c);
-      poseidon(st);
+      poseidon_fast(st);
       if (__builtin_clzll(st[7].v | 1) >= cfg.pow_bits && (st[7].v >> (64 - cfg.pow_bits)) == 0) { if ((u64)c < best) best = (u64)c; }
     }
     found = best;

@@ -160,6 +160,70 @@ HD void poseidon_mds(u64 s[12]) {
   }
 }
 
+#ifndef __CUDA_ARCH__
+// Host path (Fiat-Shamir challenger: every opening is absorbed, ~10^4 field elements per proof).  Full rounds use
+// 128-bit accumulators for the MDS layer; the 22 partial rounds run in the O(t)-per-round form whose constants
+// tools/gen_poseidon_fast.py derives and checks against the plain permutation (poseidon_fast.inc).
+static const u64 h_poseidon_fast[639] = {
+#include "poseidon_fast.inc"
+    SBN_POSEIDON_FAST_LIST};
+// Branch-free arithmetic on arbitrary 64-bit representatives (carry / borrow of random operands is unpredictable, a
+// mispredicted branch costs more than the whole reduction); only the permutation's outputs are canonicalised.
+static inline u64 h_add(u64 a, u64 b) {
+  u64 s, t; u64 c = __builtin_add_overflow(a, b, &s);
+  u64 c2 = __builtin_add_overflow(s, (0 - c) & GL_EPS, &t);
+  return t + ((0 - c2) & GL_EPS);
+}
+static inline u64 h_red(unsigned __int128 x) {   // 2^64 = 2^32 - 1, 2^96 = -1 (mod p)
+  u64 lo = (u64)x, hi = (u64)(x >> 64), hh = hi >> 32, hl = hi & GL_EPS, t0, s;
+  u64 bw = __builtin_sub_overflow(lo, hh, &t0); t0 -= (0 - bw) & GL_EPS;
+  u64 c = __builtin_add_overflow(t0, (hl << 32) - hl, &s);
+  return s + ((0 - c) & GL_EPS);
+}
+static inline u64 h_mul(u64 a, u64 b) { return h_red((unsigned __int128)a * b); }
+static inline u64 h_sbox(u64 x) { u64 x2 = h_mul(x, x), x3 = h_mul(x2, x), x4 = h_mul(x2, x2); return h_mul(x3, x4); }
+static inline void h_mds(u64 s[12]) {
+  static const u64 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  u64 o[12];
+  for (int k = 0; k < 12; k++) {
+    unsigned __int128 acc = k == 0 ? (unsigned __int128)s[0] * 8 : 0;
+    for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + k) % 12] * C[i];   // < 2^64 * 284
+    o[k] = h_red(acc);
+  }
+  for (int k = 0; k < 12; k++) s[k] = o[k];
+}
+static inline void poseidon_permute_host(u64 s[12]) {
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 12; i++) s[i] = h_sbox(h_add(s[i], h_poseidon_rc[12 * r + i]));
+    h_mds(s);
+  }
+  const u64* f = h_poseidon_fast;
+  for (int r = 0; r < 22; r++, f += 23) {
+    const u64 x0 = h_sbox(h_add(s[0], f[0]));
+    // s0' = 25 x0 + v . s[1..];  s_i' = s_i + u_i x0     (sums of reduced 64-bit products: no 128-bit overflow)
+    unsigned __int128 acc = (unsigned __int128)x0 * 25;
+    for (int i = 0; i < 11; i++) acc += h_mul(f[1 + i], s[1 + i]);
+    for (int i = 0; i < 11; i++) s[1 + i] = h_add(s[1 + i], h_mul(f[12 + i], x0));
+    s[0] = h_red(acc);
+  }
+  {  // true state = diag(1, D^) x + e
+    u64 o[11];
+    for (int i = 0; i < 11; i++) {
+      unsigned __int128 acc = f[121 + 1 + i];
+      for (int j = 0; j < 11; j++) acc += h_mul(f[11 * i + j], s[1 + j]);
+      o[i] = h_red(acc);
+    }
+    s[0] = h_add(s[0], f[121]);
+    for (int i = 0; i < 11; i++) s[1 + i] = o[i];
+  }
+  for (int r = 26; r < 30; r++) {
+    for (int i = 0; i < 12; i++) s[i] = h_sbox(h_add(s[i], h_poseidon_rc[12 * r + i]));
+    h_mds(s);
+  }
+  for (int i = 0; i < 12; i++) s[i] = s[i] >= GL_P ? s[i] - GL_P : s[i];
+}
+#endif
+
 // Canonical in, canonical out.
 HD void poseidon_permute(u64 s[12]) {
 #ifdef __CUDA_ARCH__
@@ -224,11 +288,6 @@ HD void poseidon_permute(u64 s[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 #else
-  for (int r = 0; r < 30; r++) {
-    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_RC(12 * r + i));
-    if (r < 4 || r >= 26) { for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]); }
-    else s[0] = poseidon_sbox(s[0]);
-    poseidon_mds(s);
-  }
+  poseidon_permute_host(s);
 #endif
 }

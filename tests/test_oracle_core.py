@@ -29,6 +29,15 @@ def test_poseidon_matches_python_definition(orc):
         assert [int(x) for x in orc.poseidon(np.array(st, dtype=np.uint64))] == g.permute(st, rc)
 
 
+def test_poseidon_fast_form_equals_plain_rounds(orc):
+    """The O(t)-per-round partial rounds (oracle sponge / challenger, product host challenger) vs the plain definition."""
+    rng = np.random.default_rng(7)
+    edge = [[0] * 12, [P - 1] * 12, [P - 1, 0, 1, 2**32 - 1, 2**32, 2**63, P - 2, 5, P - 1, P - 1, 0, 0]]
+    for t in range(500):
+        st = np.array(edge[t], dtype=np.uint64) if t < len(edge) else rng.integers(0, P, size=12, dtype=np.uint64)
+        assert (orc.poseidon_fast(st) == orc.poseidon(st)).all(), t
+
+
 def test_field_constants(orc):
     L = orc.lib()
     # generator pair pinned through plonky2's extension constants (DESIGN.md U1): [0, 15659105665374529263]^2 = 7 * e^2
