@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--air", default="g1", choices=sorted(AIRS))
+    ap.add_argument("--inflight", type=int, default=3, help="independent proofs in flight per GPU (one context + CUDA stream each)")
     args = ap.parse_args()
     select_air(args.air)
     if args.impl == "reference":
@@ -135,9 +136,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sbn = entry.load_package()
     stream = torch.cuda.current_stream()
-    ctx = sbn.Context(local, stream.cuda_stream)
     from starky_bn254_b200 import sharding
-    stark = getattr(sbn, AIRS[AIR][0])(NUM_IO, ctx)
+    # Proofs are independent, so each GPU keeps `inflight` of them going: one context (= one CUDA stream + caching
+    # allocator) and one host thread per slot.  The serial sections of one proof (exponentiation chain, lookup walk,
+    # host-side Fiat-Shamir) then overlap with the wide kernels of another.  Slot 0 uses torch's current stream.
+    nslots = max(1, args.inflight)
+    ctxs = [sbn.Context(local, stream.cuda_stream if k == 0 else None) for k in range(nslots)]
+    starks = [getattr(sbn, AIRS[AIR][0])(NUM_IO, c) for c in ctxs]
+    ctx, stark = ctxs[0], starks[0]
     cfg = stark.config()
     syn = sbn.synthetic
     gen_ios = getattr(syn, AIRS[AIR][3])
@@ -153,59 +159,92 @@ def main():
     dev_ios = [t.cuda(non_blocking=True) for t in host_ios]
     torch.cuda.synchronize()
 
-    def step_resident(i):
-        tr = stark.generate_trace_device(dev_ios[i % len(dev_ios)].data_ptr())
+    host_raw = [bytes(t.numpy().tobytes()) for t in host_ios]
+
+    def step_resident(i, slot=0):
+        st = starks[slot]
+        tr = st.generate_trace_device(dev_ios[i % len(dev_ios)].data_ptr())
         res = tr.results()
-        ios = syn.fill_outputs(bytes(host_ios[i % len(host_ios)].numpy().tobytes()), res, stark.io_size, out_off)
-        pi = stark.generate_public_inputs(ios)
-        p = sbn.prove(stark, cfg, tr, pi)
+        ios = syn.fill_outputs(host_raw[i % len(host_raw)], res, st.io_size, out_off)
+        pi = st.generate_public_inputs(ios)
+        p = sbn.prove(st, cfg, tr, pi)
         tr.free()
         return p
 
-    def step_e2e(i):
+    def step_e2e(i, slot=0):
+        st = starks[slot]
         h = host_ios[i % len(host_ios)]
-        tr = stark.generate_trace_ptr(h.data_ptr(), h.numel())
+        tr = st.generate_trace_ptr(h.data_ptr(), h.numel())
         res = tr.results()
-        ios = syn.fill_outputs(bytes(h.numpy().tobytes()), res, stark.io_size, out_off)
-        pi = stark.generate_public_inputs(ios)
-        p = sbn.prove(stark, cfg, tr, pi)
+        ios = syn.fill_outputs(host_raw[i % len(host_raw)], res, st.io_size, out_off)
+        pi = st.generate_public_inputs(ios)
+        p = sbn.prove(st, cfg, tr, pi)
         tr.free()
         return p.to_bytes()
+
+    def run_steps(fn, first, count):
+        """`count` steps starting at index `first`, round-robin over the slots; returns the last result of slot 0."""
+        if nslots == 1:
+            out = None
+            for i in range(count):
+                out = fn(first + i, 0)
+            return out
+        results = [None] * nslots
+        errors = []
+
+        def work(slot):
+            try:
+                for i in range(slot, count, nslots):
+                    results[slot] = fn(first + i, slot)
+            except Exception as e:   # noqa: BLE001
+                errors.append(e)
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(nslots)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return next(r for r in results if r is not None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step_resident(i)
-    # ---- timed region: device-resident inputs ----
+    run_steps(step_resident, 0, max(args.warmup, nslots))
+    # ---- timed region: device-resident inputs, `inflight` proofs overlapped ----
     sampler = ClockSampler(local)
     sampler.start()
-    ctx.kernel_timing(True)
-    launches0 = ctx.launch_count
+    launches0 = sum(c.launch_count for c in ctxs)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    proof = None
-    for i in range(args.steps):
-        proof = step_resident(args.warmup + i)
+    run_steps(step_resident, args.warmup, args.steps)   # every slot's last call has synchronised its stream
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
+    launches = sum(c.launch_count for c in ctxs) - launches0
+    # ---- per-kernel CUDA-event timing: the same steps, one proof at a time on slot 0's stream (overlap would blur it) ----
+    ctx.kernel_timing(True)
+    proof = None
+    ksteps = min(args.steps, 3)
+    k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for i in range(ksteps):
+        proof = step_resident(args.warmup + i, 0)
+    k1.record(stream)
+    torch.cuda.synchronize()
+    serial_ms_per_step = k0.elapsed_time(k1) / ksteps
     kstats = ctx.kernel_stats()
     ctx.kernel_timing(False)
     phases = proof.timings
     # ---- end-to-end: pinned host inputs -> proof bytes on the host ----
-    step_e2e(0)
+    run_steps(step_e2e, 0, nslots)
     barrier()
     t0 = time.perf_counter()
-    nbytes = 0
-    last_proof_bytes = b""
-    for i in range(args.steps):
-        last_proof_bytes = step_e2e(args.warmup + i)
-        nbytes = len(last_proof_bytes)
+    last_proof_bytes = run_steps(step_e2e, args.warmup, args.steps)
+    nbytes = len(last_proof_bytes)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -225,7 +264,7 @@ def main():
     leaf = kstats.get("merkle_leaf_hash", {"ms": 0, "count": 1})
     leaf_bytes_per_proof = (stark.num_columns + nz + 4) * L * 8 + 3 * L * 32   # LDE rows read + digests written
     leaf_launches = max(leaf["count"], 1)
-    achieved = (leaf_bytes_per_proof * args.steps / leaf_launches) / (leaf["ms"] / leaf_launches / 1e3) / 1e9 if leaf["ms"] else None
+    achieved = (leaf_bytes_per_proof * ksteps / leaf_launches) / (leaf["ms"] / leaf_launches / 1e3) / 1e9 if leaf["ms"] else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -238,7 +277,7 @@ def main():
         "metric": METRIC, "value": world * args.steps / (ms_total / 1e3), "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (Goldilocks field; BN254 Fq on 8x32-bit limbs)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "instances_per_proof": NUM_IO, "parallelism": "independent proofs, 1 process per GPU, no collective",
+        "config": {"workload": WORKLOAD, "instances_per_proof": NUM_IO, "parallelism": "independent proofs, 1 process per GPU, no collective; %d proofs in flight per GPU (one CUDA stream each)" % nslots,
                    "l2_policy": "per-proof working set ~5 GB >> 126 MB L2 (no flush needed)"},
         "instances_per_s": world * args.steps * NUM_IO / (ms_total / 1e3),
         "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": NUM_IO * stark.io_size + stark.num_public_inputs * 8,
@@ -249,10 +288,11 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon Merkle leaves)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "note": "kernel is INT-pipe bound (Poseidon ~ 2e4 integer ops per 64 B absorbed); see int_pipe",
+                     "note": "kernel is INT-pipe bound (Poseidon ~ 2e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
                      "share_of_kernel_time": leaf["ms"] / total_kernel_ms if total_kernel_ms else None},
-        "int_pipe": {"poseidon_perms_per_s": perms_per_proof * args.steps / (leaf["ms"] / 1e3) if leaf["ms"] else None, "perms_per_proof": perms_per_proof},
-        "kernel_ms_per_proof": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
+        "int_pipe": {"poseidon_perms_per_s": perms_per_proof * ksteps / (leaf["ms"] / 1e3) if leaf["ms"] else None, "perms_per_proof": perms_per_proof},
+        "serial_ms_per_step": serial_ms_per_step,
+        "kernel_ms_per_proof": {k: round(v["ms"] / ksteps, 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
         "phase_ms_last_proof": {k: round(v, 3) for k, v in phases.items()},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -21,6 +21,9 @@ static __constant__ u64 d_poseidon_rc[372] = {SBN_POSEIDON_RC_LIST, 0, 0, 0, 0, 
 #endif
 
 #ifdef __CUDACC__
+static __constant__ u32 d_poseidon_rc_l22[372 * 3] = {
+#include "poseidon_rc_l22.inc"
+    SBN_POSEIDON_RC_L22_LIST};
 // MDS coefficients as run-time constant-bank operands: with literal constants ptxas strength-reduces the
 // products into 64-bit shift/add chains, which more than doubles the instruction count of the MDS layer.
 static __constant__ u32 d_mds_c[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20, 8};
@@ -32,43 +35,32 @@ static __constant__ u32 d_mds_c[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34
 #endif
 
 #ifdef __CUDA_ARCH__
-// a * b mod p as an arbitrary 64-bit representative; a, b arbitrary u64.
-__device__ __forceinline__ u64 gl_mul_nc(u64 a, u64 b) {
-  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+// (x3:x2:x1:x0) mod p as an arbitrary 64-bit representative, using 2^64 = 2^32 - 1 and 2^96 = -1:
+//   T = (x1:x0) - (x2 + x3) + x2 * 2^32  lies in (-2^33, 2^65 - 2^33]; its 64-bit wrap count d in {-1, 0, 1} is the
+//   carry of the addition plus the (negative) borrow of the subtraction, and T - d * 2^64 + d * (2^32 - 1) cannot wrap again.
+// 11 instructions; the 128-bit product itself is left to the compiler (3 IMAD.WIDE + 1 IMAD.WIDE.X).
+__device__ __forceinline__ u64 gl_reduce128_nc(u64 lo, u64 hi) {
   u32 r0, r1;
   asm("{\n\t"
-      ".reg .u32 x0, x1, x2, x3, m, c, bw;\n\t"
-      // 128-bit product x3:x2:x1:x0
-      "mul.lo.u32 x0, %2, %4;\n\t"
-      "mul.hi.u32 x1, %2, %4;\n\t"
-      "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
-      "madc.hi.u32 x2, %2, %5, 0;\n\t"
-      "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
-      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
-      "addc.u32 x3, 0, 0;\n\t"
-      "mad.lo.cc.u32 x2, %3, %5, x2;\n\t"
-      "madc.hi.u32 x3, %3, %5, x3;\n\t"
-      // t = (x1:x0) - x3            (2^96 = -1); a borrow wraps by 2^64 = EPS
-      "sub.cc.u32 x0, x0, x3;\n\t"
-      "subc.cc.u32 x1, x1, 0;\n\t"
-      "subc.u32 m, 0, 0;\n\t"
-      "sub.cc.u32 x0, x0, m;\n\t"
-      "subc.u32 x1, x1, 0;\n\t"
-      // r = t + x2 * (2^32 - 1)     (2^64 = 2^32 - 1)
-      "add.cc.u32 x1, x1, x2;\n\t"
-      "addc.u32 c, 0, 0;\n\t"
-      "sub.cc.u32 x0, x0, x2;\n\t"
-      "subc.cc.u32 x1, x1, 0;\n\t"
-      "subc.u32 bw, 0, 0;\n\t"
-      "add.u32 c, c, bw;\n\t"        // net wrap count: 0 or 1
-      "neg.s32 c, c;\n\t"            // 0 or 0xFFFFFFFF (= EPS)
-      "add.cc.u32 %0, x0, c;\n\t"
-      "addc.u32 %1, x1, 0;\n\t"
+      ".reg .u32 s, cs, b, d, e, f;\n\t"
+      "add.cc.u32 s, %4, %5;\n\t"        // x2 + x3 = cs:s
+      "addc.u32 cs, 0, 0;\n\t"
+      "sub.cc.u32 %0, %2, s;\n\t"
+      "subc.cc.u32 %1, %3, cs;\n\t"
+      "subc.u32 b, 0, 0;\n\t"            // 0 or -1
+      "add.cc.u32 %1, %1, %4;\n\t"       // + x2 * 2^32
+      "addc.u32 d, b, 0;\n\t"            // d = carry + b
+      "neg.s32 e, d;\n\t"                // d * (2^32 - 1) as a two's-complement 64-bit value f:e
+      "shr.s32 f, d, 31;\n\t"
+      "add.cc.u32 %0, %0, e;\n\t"
+      "addc.u32 %1, %1, f;\n\t"
       "}"
-      : "=r"(r0), "=r"(r1)
-      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
   return ((u64)r1 << 32) | r0;
 }
+// a * b mod p as an arbitrary 64-bit representative; a, b arbitrary u64.
+__device__ __forceinline__ u64 gl_mul_nc(u64 a, u64 b) { return gl_reduce128_nc(a * b, __umul64hi(a, b)); }
 // a + b mod p, a arbitrary u64, b canonical (< p); result arbitrary u64 representative.
 __device__ __forceinline__ u64 gl_add_nc(u64 a, u64 b) {
   u32 r0, r1;
@@ -91,43 +83,54 @@ __device__ __forceinline__ u64 poseidon_sbox_nc(u64 x) {
   return gl_mul_nc(x3, x4);
 }
 // s <- MDS * s + rc[rc_off ..] (the next round's constants; offset 360 = zeros), lanes arbitrary u64 in and out.
+// Each lane is cut into limbs of 22 + 22 + 20 bits, so every product with an MDS coefficient (<= 41, row sum 284)
+// and the whole 12-term sum plus the constant's limb stay below 2^32: the layer is 3 * 145 native 32-bit
+// multiply-adds (IMAD issues at twice the rate of IMAD.WIDE on sm_100, tools/microbench/int_throughput.cu)
+// followed by one carry-chain recombination per lane:
+//   V = a0 + a1 2^22 + a2 2^44 < 2^74  ->  (w1:w0) + h 2^64,  h < 2^10,  then  + h (2^32 - 1)  with one wrap fix.
 __device__ __forceinline__ void poseidon_mds_nc(u64 s[12], int rc_off) {
-  u32 lo[12], hi[12];
+  u32 l0[12], l1[12], l2[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
+  for (int i = 0; i < 12; i++) {
+    l0[i] = (u32)s[i] & 0x3FFFFFu;
+    l1[i] = (u32)(s[i] >> 22) & 0x3FFFFFu;
+    l2[i] = (u32)(s[i] >> 44);
+  }
 #pragma unroll
   for (int k = 0; k < 12; k++) {
-    const u64 rc = d_poseidon_rc[rc_off + k];
-    u64 al = (u32)rc, ah = rc >> 32;
-    // one IMAD.WIDE per term (left to itself the compiler strength-reduces the small constants into
-    // shift/add sequences on 64-bit pairs, which more than doubles the instruction count of this layer)
+    u32 a0 = d_poseidon_rc_l22[3 * (rc_off + k)], a1 = d_poseidon_rc_l22[3 * (rc_off + k) + 1], a2 = d_poseidon_rc_l22[3 * (rc_off + k) + 2];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + k) % 12]), "r"(d_mds_c[i]));
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + k) % 12]), "r"(d_mds_c[i]));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a0) : "r"(l0[(i + k) % 12]), "r"(d_mds_c[i]));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a1) : "r"(l1[(i + k) % 12]), "r"(d_mds_c[i]));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a2) : "r"(l2[(i + k) % 12]), "r"(d_mds_c[i]));
     }
     if (k == 0) {
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[0]), "r"(d_mds_c[12]));
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[0]), "r"(d_mds_c[12]));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a0) : "r"(l0[0]), "r"(d_mds_c[12]));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a1) : "r"(l1[0]), "r"(d_mds_c[12]));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a2) : "r"(l2[0]), "r"(d_mds_c[12]));
     }
-    // value = al + ah * 2^32, al, ah < 2^42.  128-bit form: lo64 = al + (ah0 << 32), hi = ah1 + carry (< 2^11);
-    // then lo64 + hi * (2^32 - 1) with one conditional wrap fix.
     u32 r0, r1;
     asm("{\n\t"
-        ".reg .u32 l1, h, t0, t1, c;\n\t"
-        "add.cc.u32 l1, %3, %4;\n\t"      // al1 + ah0
-        "addc.u32 h, %5, 0;\n\t"          // ah1 + carry
-        "sub.cc.u32 t0, 0, h;\n\t"        // (h << 32) - h
-        "subc.u32 t1, h, 0;\n\t"
-        "add.cc.u32 %0, %2, t0;\n\t"
-        "addc.cc.u32 %1, l1, t1;\n\t"
+        ".reg .u32 p, q, y, h, el, eh, c;\n\t"
+        "shl.b32 p, %3, 22;\n\t"
+        "shr.u32 q, %3, 10;\n\t"
+        "shl.b32 y, %4, 12;\n\t"
+        "shr.u32 h, %4, 20;\n\t"
+        "add.cc.u32 %0, %2, p;\n\t"
+        "addc.cc.u32 %1, q, y;\n\t"
+        "addc.u32 h, h, 0;\n\t"             // overflow above 2^64, < 2^10
+        "mul.lo.u32 el, h, 0xFFFFFFFF;\n\t"  // h * (2^32 - 1) = eh:el
+        "mul.hi.u32 eh, h, 0xFFFFFFFF;\n\t"
+        "add.cc.u32 %0, %0, el;\n\t"
+        "addc.cc.u32 %1, %1, eh;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "neg.s32 c, c;\n\t"
+        "neg.s32 c, c;\n\t"                 // wrapped once: + (2^32 - 1); the sum was < 2^64 + 2^42, so no second wrap
         "add.cc.u32 %0, %0, c;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
         "}"
         : "=&r"(r0), "=&r"(r1)
-        : "r"((u32)al), "r"((u32)(al >> 32)), "r"((u32)ah), "r"((u32)(ah >> 32)));
+        : "r"(a0), "r"(a1), "r"(a2));
     s[k] = ((u64)r1 << 32) | r0;
   }
 }
