@@ -35,49 +35,6 @@ static __constant__ u32 d_mds_c[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34
 #endif
 
 #ifdef __CUDA_ARCH__
-// (x3:x2:x1:x0) mod p as an arbitrary 64-bit representative, using 2^64 = 2^32 - 1 and 2^96 = -1:
-//   T = (x1:x0) - (x2 + x3) + x2 * 2^32  lies in (-2^33, 2^65 - 2^33]; its 64-bit wrap count d in {-1, 0, 1} is the
-//   carry of the addition plus the (negative) borrow of the subtraction, and T - d * 2^64 + d * (2^32 - 1) cannot wrap again.
-// 11 instructions; the 128-bit product itself is left to the compiler (3 IMAD.WIDE + 1 IMAD.WIDE.X).
-__device__ __forceinline__ u64 gl_reduce128_nc(u64 lo, u64 hi) {
-  u32 r0, r1;
-  asm("{\n\t"
-      ".reg .u32 s, cs, b, d, e, f;\n\t"
-      "add.cc.u32 s, %4, %5;\n\t"        // x2 + x3 = cs:s
-      "addc.u32 cs, 0, 0;\n\t"
-      "sub.cc.u32 %0, %2, s;\n\t"
-      "subc.cc.u32 %1, %3, cs;\n\t"
-      "subc.u32 b, 0, 0;\n\t"            // 0 or -1
-      "add.cc.u32 %1, %1, %4;\n\t"       // + x2 * 2^32
-      "addc.u32 d, b, 0;\n\t"            // d = carry + b
-      "neg.s32 e, d;\n\t"                // d * (2^32 - 1) as a two's-complement 64-bit value f:e
-      "shr.s32 f, d, 31;\n\t"
-      "add.cc.u32 %0, %0, e;\n\t"
-      "addc.u32 %1, %1, f;\n\t"
-      "}"
-      : "=&r"(r0), "=&r"(r1)
-      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
-  return ((u64)r1 << 32) | r0;
-}
-// a * b mod p as an arbitrary 64-bit representative; a, b arbitrary u64.
-__device__ __forceinline__ u64 gl_mul_nc(u64 a, u64 b) { return gl_reduce128_nc(a * b, __umul64hi(a, b)); }
-// a + b mod p, a arbitrary u64, b canonical (< p); result arbitrary u64 representative.
-__device__ __forceinline__ u64 gl_add_nc(u64 a, u64 b) {
-  u32 r0, r1;
-  asm("{\n\t"
-      ".reg .u32 c;\n\t"
-      "add.cc.u32 %0, %2, %4;\n\t"
-      "addc.cc.u32 %1, %3, %5;\n\t"
-      "addc.u32 c, 0, 0;\n\t"
-      "neg.s32 c, c;\n\t"
-      "add.cc.u32 %0, %0, c;\n\t"
-      "addc.u32 %1, %1, 0;\n\t"
-      "}"
-      : "=&r"(r0), "=&r"(r1)
-      : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
-  return ((u64)r1 << 32) | r0;
-}
-__device__ __forceinline__ u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 __device__ __forceinline__ u64 poseidon_sbox_nc(u64 x) {
   u64 x2 = gl_mul_nc(x, x), x3 = gl_mul_nc(x2, x), x4 = gl_mul_nc(x2, x2);
   return gl_mul_nc(x3, x4);
