@@ -31,7 +31,7 @@ AirDesc make_air(int air_id, size_t num_io) {
       const u32 sf = 24 * 16, main_cols = sf + 14, pp = main_cols, iop = pp + 2, lookups = iop + 1 + 4 * (u32)num_io, nrc = 24 * 16 - 3;
       a.num_columns = lookups + 1 + 2 * nrc; a.num_public_inputs = 56 * num_io; a.num_rows = 512 * num_io; a.io_size = 224; a.result_words = 8;
       add_u16_pairs(a, lookups, 0, nrc);
-      a.segments.push_back({SEG_G1_CORE, (int)num_io, 0, 0, 0, 1 + 56 * num_io + 192});
+      a.segments.push_back({SEG_G1_CORE, (int)num_io, 64 + 16, (int)sf, 0, 1 + 56 * num_io + 192});
       a.segments.push_back({SEG_FLAGS, (int)sf, 0, 0, 0, 26});
       a.segments.push_back({SEG_G1_ADD, 64, (int)sf + 4, 0, 0, 165});
       a.segments.push_back({SEG_G1_DOUBLE, 64, (int)sf + 2, 0, 0, 165});

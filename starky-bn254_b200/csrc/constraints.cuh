@@ -33,12 +33,18 @@ struct QPoint {
   F z_last, l_first, l_last;
   F alpha[SBN_MAX_CHALLENGES];
   F acc[SBN_MAX_CHALLENGES];
+  // public-input binding columns at this point (see PiBinding below): pic[col * pic_stride]
+  const u64* pic; size_t pic_stride; int pic_per_chal;
+  F pi_skip[SBN_MAX_CHALLENGES];   // alpha^((num_io - 1) * io_len)
+  HD F picol(int col) const { return F(pic[(size_t)col * pic_stride]); }
   HD F lv(int c) const { return F(lp[(size_t)c * stride]); }
   HD F nv(int c) const { return F(np[(size_t)c * stride]); }
   HD void constraint(F c) {
 #pragma unroll
     for (int k = 0; k < SBN_MAX_CHALLENGES; k++) acc[k] = acc[k] * alpha[k] + c;
   }
+  // one constraint whose value differs per challenge (the folded public-input binding)
+  HD void constraint2(F c0, F c1) { acc[0] = acc[0] * alpha[0] + c0; acc[1] = acc[1] * alpha[1] + c1; }
   HD void transition(F c) { constraint(c * z_last); }
   HD void first_row(F c) { constraint(c * l_first); }
   HD void last_row(F c) { constraint(c * l_last); }
@@ -301,41 +307,45 @@ HD void eval_g1_double(QPoint& q, F filter, int o) {
   eval_g1_tail(q, filter, o, lambda, x, x, y);
 }
 
-// reference src/curves/g1/exp.rs:340-461: is_final constraint, public-input binding, transitions.
-// 1 + 56*num_io + 192 constraints.  Column map: a(32) b(32) output(320) flags(14) | periodic(2) | pulses(1+4n) | lookups
-HD void eval_g1_exp_core(QPoint& q, int num_io) {
-  const int sf = 24 * 16, out_o = 64, start_pulses = sf + 14 + 2;
-  const F one(1), base(1ULL << 16);
-  F is_add = q.lv(sf + 4), is_double = q.lv(sf + 2), is_final = q.lv(sf), is_not_final = one - is_final;
-  F sum_is_output;
-  for (int i = 1; i < 2 * num_io; i += 2) sum_is_output = sum_is_output + q.lv(start_pulses + 2 + 2 * i);
-  q.constraint(is_final - sum_is_output);
-  // row values the public inputs are compared with (u16 limb pairs -> u32, reference utils.rs:56-63)
-  F v[7][8];
-  for (int g = 0; g < 4; g++) for (int j = 0; j < 8; j++) v[g][j] = q.lv(16 * g + 2 * j) + base * q.lv(16 * g + 2 * j + 1);
-  for (int j = 0; j < 8; j++) { v[5][j] = v[2][j]; v[6][j] = v[3][j]; }
-  for (int j = 0; j < 8; j++) v[4][j] = q.lv(sf + 6 + j);
-  v[4][0] = v[4][0] * F(2) + is_add;
-  for (int i = 0; i < num_io; i++) {
-    F is_in = q.lv(start_pulses + 2 + 4 * i), is_out = q.lv(start_pulses + 4 + 4 * i);
-    const u64* io = q.pi + 56 * i;  // x.x x.y off.x off.y exp out.x out.y
-    // emission order (exp.rs:381-391): x.x, x.y, offset.x, offset.y (input), output.x, output.y (output), exp_val (input)
-    for (int g = 0; g < 4; g++) for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * g + j]) - v[g][j]));
-    for (int g = 5; g < 7; g++) for (int j = 0; j < 8; j++) q.constraint(is_out * (F(io[8 * g + j]) - v[g][j]));
-    for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[32 + j]) - v[4][j]));
+// ---- public-input binding of the exponentiation AIRs, folded over the instances ----
+// The reference emits, for every instance i, io_len constraints  pulse_{kind(u), i} * (PI_{i,u} - V_u)  (u < io_len;
+// kind = input or output pulse; V_u an expression of the local row that does not depend on i), e.g.
+// src/curves/g1/exp.rs:374-392.  Under the consumer's Horner fold (acc = acc * alpha + c) constraint (i, u) carries the
+// weight a_i * alpha^(io_len - 1 - u) * alpha^(#later constraints) with a_i = alpha^((n - 1 - i) io_len), so the whole
+// block equals io_len "virtual" constraints
+//        W_u = U_u(x) - V_u(x) * S_kind(u)(x),   U_u = sum_i a_i PI_{i,u} pulse_{kind(u), i},   S_kind = sum_i a_i pulse_{kind, i}
+// folded after multiplying the accumulator by alpha^((n - 1) io_len).  On the trace domain a pulse column is 1 at its
+// row and 0 elsewhere, so U_u and S_kind are the low-degree extensions of SPARSE columns (a_i PI_{i,u} at the pulse
+// rows): the prover builds those io_len + 2 columns per challenge (+ one shared column, the plain sum of the output
+// pulses), transforms them with the NTT kernels and hands their values at this point in `q.pic`:
+//   col 0: sum_i pulse_out_i;  per challenge c: base = 1 + c * (io_len + 2): S_in, S_out, U_0 .. U_{io_len-1}.
+// Same field element as the reference's n * io_len constraints, at 1/n of the per-point work.
+// emission index u -> (index inside the instance's public-input record, pulse kind 0 = input / 1 = output).
+// group_count: G for the u32 cores (Fq 1, G1 2, G2 4); 0 = Fq12 (io record 584), -1 = Fq12 with u64 exponent (577).
+HD void pi_map(int group_count, int u, int& pi, int& kind) {
+  if (group_count > 0) {
+    const int G = group_count;
+    if (u < 16 * G) { pi = u; kind = 0; }
+    else if (u < 24 * G) { pi = u + 8; kind = 1; }
+    else { pi = u - 8 * G; kind = 0; }
+  } else {
+    const int out_off = group_count == 0 ? 392 : 385;
+    if (u >= 576) { pi = 384 + (u - 576); kind = 0; return; }
+    const int c = u / 48, r = u % 48;
+    if (r < 16) { pi = 16 * c + r; kind = 0; }
+    else if (r < 32) { pi = 192 + 16 * c + (r - 16); kind = 0; }
+    else { pi = out_off + 16 * c + (r - 32); kind = 1; }
   }
-  // transitions (exp.rs:393-461)
-  F f1 = is_not_final * is_double, f2 = is_not_final * is_add, f3 = is_not_final * (one - is_double - is_add);
-  // is_double: next_a = output.new, next_b = b
-  for (int i = 0; i < 16; i++) q.transition(f1 * (q.nv(i) - q.lv(out_o + G1O_NEW_X + i)));
-  for (int i = 0; i < 16; i++) q.transition(f1 * (q.nv(16 + i) - q.lv(out_o + G1O_NEW_Y + i)));
-  for (int i = 0; i < 32; i++) q.transition(f1 * (q.nv(32 + i) - q.lv(32 + i)));
-  // is_add: next_a = a, next_b = output.new
-  for (int i = 0; i < 32; i++) q.transition(f2 * (q.nv(i) - q.lv(i)));
-  for (int i = 0; i < 16; i++) q.transition(f2 * (q.nv(32 + i) - q.lv(out_o + G1O_NEW_X + i)));
-  for (int i = 0; i < 16; i++) q.transition(f2 * (q.nv(48 + i) - q.lv(out_o + G1O_NEW_Y + i)));
-  // neither: next = current
-  for (int i = 0; i < 64; i++) q.transition(f3 * (q.nv(i) - q.lv(i)));
+}
+HD int pi_io_len(int group_count) { return group_count > 0 ? (3 * group_count + 1) * 8 : (group_count == 0 ? 584 : 577); }
+HD void pi_virtual(QPoint& q, int u, int kind, F v) {
+  const int b0 = 1, b1 = 1 + q.pic_per_chal;
+  q.constraint2(q.picol(b0 + 2 + u) - v * q.picol(b0 + kind), q.picol(b1 + 2 + u) - v * q.picol(b1 + kind));
+}
+HD void pi_begin(QPoint& q, F is_final) {
+  q.constraint(is_final - q.picol(0));
+#pragma unroll
+  for (int k = 0; k < SBN_MAX_CHALLENGES; k++) q.acc[k] = q.acc[k] * q.pi_skip[k];
 }
 
 // ---- generic exponentiation-AIR core for the AIRs whose public inputs are u32 limbs (Fq, G1, G2) ----
@@ -343,29 +353,19 @@ HD void eval_g1_exp_core(QPoint& q, int num_io) {
 // is_final constraint, public-input binding, a/b transitions.  The row starts with a (G groups of 16 limbs)
 // and b (G groups); `newv` is the column of the G-group value the operation produces (Fq: output, G1/G2:
 // new_x | new_y); per-io public inputs are x[G][8] offset[G][8] exp_val[8] output[G][8].
-// 1 + (3G + 1) * 8 * num_io + 3 * 32 * G constraints.  G = 2 is exactly eval_g1_exp_core.
+// 1 + (3G + 1) * 8 * num_io + 3 * 32 * G constraints.
 template <int G> HD void eval_exp_core_u32(QPoint& q, int num_io, int newv, int sf) {
-  const int start_pulses = sf + 14 + 2;
   const F one(1), base(1ULL << 16);
   F is_add = q.lv(sf + 4), is_double = q.lv(sf + 2), is_final = q.lv(sf), is_not_final = one - is_final;
-  F sum_is_output;
-  for (int i = 1; i < 2 * num_io; i += 2) sum_is_output = sum_is_output + q.lv(start_pulses + 2 + 2 * i);
-  q.constraint(is_final - sum_is_output);
-  F va[G][8], vb[G][8], ve[8];
-  for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) {
-    va[g][j] = q.lv(16 * g + 2 * j) + base * q.lv(16 * g + 2 * j + 1);
-    vb[g][j] = q.lv(16 * (G + g) + 2 * j) + base * q.lv(16 * (G + g) + 2 * j + 1);
-  }
-  for (int j = 0; j < 8; j++) ve[j] = q.lv(sf + 6 + j);
-  ve[0] = ve[0] * F(2) + is_add;
-  const int io_len = (3 * G + 1) * 8;
-  for (int i = 0; i < num_io; i++) {
-    F is_in = q.lv(start_pulses + 2 + 4 * i), is_out = q.lv(start_pulses + 4 + 4 * i);
-    const u64* io = q.pi + (size_t)io_len * i;
-    for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * g + j]) - va[g][j]));
-    for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * (G + g) + j]) - vb[g][j]));
-    for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) q.constraint(is_out * (F(io[8 * (2 * G + 1 + g) + j]) - vb[g][j]));
-    for (int j = 0; j < 8; j++) q.constraint(is_in * (F(io[8 * 2 * G + j]) - ve[j]));
+  pi_begin(q, is_final);
+  // emission order per instance: x groups (input pulse), offset groups (input), output groups (output pulse), exp_val (input)
+  for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) pi_virtual(q, 8 * g + j, 0, q.lv(16 * g + 2 * j) + base * q.lv(16 * g + 2 * j + 1));
+  for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) pi_virtual(q, 8 * (G + g) + j, 0, q.lv(16 * (G + g) + 2 * j) + base * q.lv(16 * (G + g) + 2 * j + 1));
+  for (int g = 0; g < G; g++) for (int j = 0; j < 8; j++) pi_virtual(q, 8 * (2 * G + g) + j, 1, q.lv(16 * (G + g) + 2 * j) + base * q.lv(16 * (G + g) + 2 * j + 1));
+  for (int j = 0; j < 8; j++) {
+    F limb = q.lv(sf + 6 + j);
+    if (j == 0) limb = limb * F(2) + is_add;
+    pi_virtual(q, 24 * G + j, 0, limb);
   }
   const int W = 16 * G;
   F f1 = is_not_final * is_double, f2 = is_not_final * is_add, f3 = is_not_final * (one - is_double - is_add);
@@ -489,33 +489,26 @@ HD void fq12_product_acc(const QPoint& q, int xa, int ya, int oi, F* acc /*31*/)
   }
 }
 // reference src/fields/fq12/exp.rs:340-393 (u64 variant: src/fields/fq12_u64/exp_u64.rs:331-383): is_final, public inputs
-// (u16 limbs: x[12][16] offset[12][16] exp output[12][16]), transitions.  1 + io_len * num_io + 6 * 192 constraints.
+// (u16 limbs: x[12][16] offset[12][16] exp output[12][16]), transitions.  1 + io_len * num_io + 6 * 192 constraints;
+// the public-input block is folded over the instances as described above (emission order per instance: for each
+// coefficient c: x[c] (input pulse), offset[c] (input), output[c] (output pulse); then the exponent (input)).
 HD void eval_fq12_exp_core(QPoint& q, int num_io, int sf, bool u64_variant) {
-  const int nflags = u64_variant ? 6 : 14;
-  const int start_pulses = sf + nflags + (u64_variant ? 0 : 2);
   const int is_sq_c = u64_variant ? sf + 1 : sf + 2, is_mul_c = u64_variant ? sf + 3 : sf + 4;
-  const int io_len = u64_variant ? 577 : 584, out_off = u64_variant ? 385 : 392;
   const F one(1);
   F is_mul = q.lv(is_mul_c), is_sq = q.lv(is_sq_c), is_final = q.lv(sf), is_not_final = one - is_final;
-  F sum_is_output;
-  for (int i = 1; i < 2 * num_io; i += 2) sum_is_output = sum_is_output + q.lv(start_pulses + 2 + 2 * i);
-  q.constraint(is_final - sum_is_output);
-  for (int i = 0; i < num_io; i++) {
-    F is_in = q.lv(start_pulses + 2 + 4 * i), is_out = q.lv(start_pulses + 4 + 4 * i);
-    const u64* io = q.pi + (size_t)io_len * i;
-    for (int c = 0; c < 12; c++) {
-      for (int j = 0; j < 16; j++) q.constraint(is_in * (F(io[16 * c + j]) - q.lv(16 * c + j)));
-      for (int j = 0; j < 16; j++) q.constraint(is_in * (F(io[192 + 16 * c + j]) - q.lv(192 + 16 * c + j)));
-      for (int j = 0; j < 16; j++) q.constraint(is_out * (F(io[out_off + 16 * c + j]) - q.lv(192 + 16 * c + j)));
-    }
-    if (u64_variant) {
-      q.constraint(is_in * (F(io[384]) - (q.lv(sf + 5) * F(2) + is_mul)));
-    } else {
-      for (int j = 0; j < 8; j++) {
-        F limb = q.lv(sf + 6 + j);
-        if (j == 0) limb = limb * F(2) + is_mul;
-        q.constraint(is_in * (F(io[384 + j]) - limb));
-      }
+  pi_begin(q, is_final);
+  for (int c = 0; c < 12; c++) {
+    for (int j = 0; j < 16; j++) pi_virtual(q, 48 * c + j, 0, q.lv(16 * c + j));
+    for (int j = 0; j < 16; j++) pi_virtual(q, 48 * c + 16 + j, 0, q.lv(192 + 16 * c + j));
+    for (int j = 0; j < 16; j++) pi_virtual(q, 48 * c + 32 + j, 1, q.lv(192 + 16 * c + j));
+  }
+  if (u64_variant) {
+    pi_virtual(q, 576, 0, q.lv(sf + 5) * F(2) + is_mul);
+  } else {
+    for (int j = 0; j < 8; j++) {
+      F limb = q.lv(sf + 6 + j);
+      if (j == 0) limb = limb * F(2) + is_mul;
+      pi_virtual(q, 576 + j, 0, limb);
     }
   }
   F f1 = is_not_final * is_sq, f2 = is_not_final * is_mul, f3 = is_not_final * (one - is_sq - is_mul);

@@ -19,7 +19,8 @@ HD void qpoint_begin(const QArgs& a, size_t idx, QPoint& q) {
   q.z_last = x - F(a.w_inv);
   q.l_first = F(a.lagrange[a.coset_off[bq] + k]);
   q.l_last = F(a.lagrange[a.lagrange_stride + a.coset_off[bq] + k]);
-  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) { q.alpha[c] = F(a.alpha[c]); q.acc[c] = F(); }
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) { q.alpha[c] = F(a.alpha[c]); q.acc[c] = F(); q.pi_skip[c] = F(a.pi_skip[c]); }
+  q.pic = a.pi_lde + idx; q.pic_stride = N << 1; q.pic_per_chal = a.pi_per_chal;
 }
 HD void qpoint_end(const QArgs& a, size_t idx, const QPoint& q) {
   const size_t N2 = size_t(2) << a.logn;
@@ -57,7 +58,7 @@ HD void eval_segment(const QArgs& a, const Segment& s, size_t idx, QPoint& q) {
   switch (s.kind) {
     case SEG_SPLIT_RANGE_CHECK: eval_split_u16_range_check(q, s.p0, s.p1, s.p2); break;
     case SEG_MODULAR_CORE: eval_modular_stark_core(q); break;
-    case SEG_G1_CORE: eval_g1_exp_core(q, s.p0); break;
+    case SEG_G1_CORE: eval_exp_core_u32<2>(q, s.p0, s.p1, s.p2); break;
     case SEG_FLAGS: eval_flags(q, s.p0); break;
     case SEG_G1_ADD: eval_g1_add(q, q.lv(s.p1), s.p0); break;
     case SEG_G1_DOUBLE: eval_g1_double(q, q.lv(s.p1), s.p0); break;
@@ -133,6 +134,55 @@ static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
   LAUNCH_CHECK(ctx);
 }
 
+// Sparse public-input binding columns (constraints.cuh "public-input binding ... folded over the instances"):
+// vals[col][row], col 0 = sum of output pulses; per challenge c: 1 + c * (io_len + 2) + {0: S_in, 1: S_out, 2 + u: U_u}.
+__global__ void k_pi_columns(u64* __restrict__ vals, size_t N, const u64* __restrict__ pi, const u64* __restrict__ a /* [chal][num_io] */, int num_io,
+                             int rows_per_io, int group_count, int num_challenges) {
+  const int io_len = pi_io_len(group_count), per = io_len + 2;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (w >= per) return;
+  const size_t pos_in = (size_t)i * rows_per_io, pos_out = pos_in + rows_per_io - 1;
+  if (w == 0) vals[pos_out] = 1;
+  for (int c = 0; c < num_challenges; c++) {
+    const u64 ai = a[(size_t)c * num_io + i];
+    u64* col = vals + (size_t)(1 + c * per + w) * N;
+    if (w == 0) col[pos_in] = ai;
+    else if (w == 1) col[pos_out] = ai;
+    else {
+      int pidx, kind;
+      pi_map(group_count, w - 2, pidx, kind);
+      col[kind ? pos_out : pos_in] = gl_mul(ai, pi[(size_t)i * io_len + pidx]);
+    }
+  }
+}
+// Returns the low-degree extension of the binding columns on the two quotient cosets: out[col][bq][k].
+static void build_pi_binding(sbn_ctx* ctx, QArgs& a, const Segment& core, const u64* d_public_inputs, int num_challenges, DevBuf<u64>& lde) {
+  const int group_count = core.kind == SEG_FQ_CORE ? 1 : core.kind == SEG_G1_CORE ? 2 : core.kind == SEG_G2_CORE ? 4 : (core.p2 ? -1 : 0);
+  num_challenges = SBN_MAX_CHALLENGES;   // unused challenges have alpha = 0; their columns exist so the kernel never reads out of bounds
+  const int num_io = core.p0, io_len = pi_io_len(group_count), per = io_len + 2, ncols = 1 + num_challenges * per;
+  const int logn = a.logn; const size_t N = size_t(1) << logn;
+  const int rows_per_io = (int)(N / num_io);
+  KScope ks(ctx, "q_pi_binding");
+  std::vector<u64> ha((size_t)num_challenges * num_io);
+  for (int c = 0; c < num_challenges; c++) {
+    const u64 step = gl_pow(a.alpha[c], (u64)io_len);
+    u64 v = 1;
+    for (int i = num_io - 1; i >= 0; i--) { ha[(size_t)c * num_io + i] = v; v = gl_mul(v, step); }   // a_i = alpha^((n-1-i) io_len)
+    a.pi_skip[c] = ha[(size_t)c * num_io];                                                            // alpha^((n-1) io_len)
+  }
+  DevBuf<u64> d_a(ctx, ha.size()), vals(ctx, (size_t)ncols * N), coeffs(ctx, (size_t)ncols * N);
+  CUDA_CHECK(cudaMemcpyAsync(d_a, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(vals, 0, (size_t)ncols * N * 8, ctx->stream));
+  k_pi_columns<<<dim3((per + 63) / 64, num_io), 64, 0, ctx->stream>>>(vals, N, d_public_inputs, d_a, num_io, rows_per_io, group_count, num_challenges);
+  LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `ha` is pageable host memory
+  intt_columns(ctx, vals, coeffs, ncols, logn);
+  lde = DevBuf<u64>(ctx, (size_t)ncols * 2 * N);
+  for (int bq = 0; bq < 2; bq++)
+    ntt_batch(ctx, coeffs, N, lde + (size_t)bq * N, 2 * N, ncols, logn, false, get_pow_table(ctx, a.coset_shift[bq], logn), nullptr);
+  a.pi_lde = lde; a.pi_per_chal = per;
+}
+
 __global__ void k_fill_lagrange_coeffs(u64* coeffs, const u64* wpow, u64 ninv, size_t N) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= N) return;
@@ -191,7 +241,10 @@ void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_
     a.perm_lhs = d_lhs; a.perm_rhs = d_rhs; a.perm_gamma = d_gamma; a.perm_batch = perm.batch_size; a.nz = (int)perm.nz();
     segs.push_back({SEG_PERMUTATION, 0, 0, 0, 0, 2 * perm.nz()});
   }
-  DevBuf<u64> scratch;
+  DevBuf<u64> scratch, pi_lde;
+  a.pi_lde = acc; a.pi_per_chal = 0;   // valid pointer for AIRs without a public-input block (never dereferenced there)
+  for (const Segment& s : segs)
+    if (s.kind == SEG_FQ_CORE || s.kind == SEG_G1_CORE || s.kind == SEG_G2_CORE || s.kind == SEG_FQ12_CORE) build_pi_binding(ctx, a, s, d_public_inputs, num_challenges, pi_lde);
   for (const Segment& s : segs) if (s.kind == SEG_FQ12_MUL && !scratch.p) scratch = DevBuf<u64>(ctx, (size_t)12 * 31 * 2 * N);
   a.scratch = scratch.p;
   bool first = true;

@@ -28,6 +28,8 @@ struct QArgs {
   // permutation segment
   const u32* perm_lhs; const u32* perm_rhs; const u64* perm_gamma; int perm_batch; int nz;
   u64* scratch;                              // Fq12 product limb polynomials [12*31][2N] (SEG_FQ12_MUL only)
+  const u64* pi_lde; int pi_per_chal;        // public-input binding columns on the quotient cosets [col][bq][k] (core segments)
+  u64 pi_skip[SBN_MAX_CHALLENGES];           // alpha^((num_io - 1) * io_len)
 };
 
 // Evaluates every constraint of `air` (+ the permutation checks) on the size-2N quotient coset and

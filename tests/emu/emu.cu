@@ -22,10 +22,33 @@ int emu_eval_air(int air_id, size_t num_io, const u64* lv, const u64* nv, const 
       q.lp = lv; q.np = nv; q.stride = 1; q.pi = pi;
       q.z_last = F(z_last); q.l_first = F(l_first); q.l_last = F(l_last);
       for (int c = 0; c < 2; c++) { q.alpha[c] = F(alphas[c]); q.acc[c] = F(); }
+      // public-input binding columns at this point: what the prover's sparse-column LDEs evaluate to, i.e. the same linear
+      // combinations of the row's pulse columns (quotient.cu build_pi_binding / k_pi_columns)
+      std::vector<u64> pic(1, 0);
+      q.pic = pic.data(); q.pic_stride = 1; q.pic_per_chal = 0;
+      if (s.kind == SEG_FQ_CORE || s.kind == SEG_G1_CORE || s.kind == SEG_G2_CORE || s.kind == SEG_FQ12_CORE) {
+        const int gc = s.kind == SEG_FQ_CORE ? 1 : s.kind == SEG_G1_CORE ? 2 : s.kind == SEG_G2_CORE ? 4 : (s.p2 ? -1 : 0);
+        const int sf = s.kind == SEG_FQ12_CORE ? s.p1 : s.p2;
+        const int start_pulses = sf + (gc == -1 ? 6 : 16), n = s.p0, io_len = pi_io_len(gc), per = io_len + 2;
+        pic.assign(1 + 2 * per, 0);
+        for (int i = 0; i < n; i++) pic[0] = gl_add(pic[0], lv[start_pulses + 4 + 4 * i]);
+        for (int c = 0; c < 2; c++) {
+          u64 step = gl_pow(alphas[c], (u64)io_len);
+          q.pi_skip[c] = F(gl_pow(step, (u64)(n - 1)));
+          for (int i = 0; i < n; i++) {
+            u64 ai = gl_pow(step, (u64)(n - 1 - i));
+            u64 pin = lv[start_pulses + 2 + 4 * i], pout = lv[start_pulses + 4 + 4 * i];
+            u64* col = pic.data() + 1 + c * per;
+            col[0] = gl_add(col[0], gl_mul(ai, pin)); col[1] = gl_add(col[1], gl_mul(ai, pout));
+            for (int u = 0; u < io_len; u++) { int pidx, kind; pi_map(gc, u, pidx, kind); col[2 + u] = gl_add(col[2 + u], gl_mul(gl_mul(ai, pi[(size_t)i * io_len + pidx]), kind ? pout : pin)); }
+          }
+        }
+        q.pic = pic.data(); q.pic_per_chal = per;
+      }
       switch (s.kind) {
         case SEG_SPLIT_RANGE_CHECK: eval_split_u16_range_check(q, s.p0, s.p1, s.p2); break;
         case SEG_MODULAR_CORE: eval_modular_stark_core(q); break;
-        case SEG_G1_CORE: eval_g1_exp_core(q, s.p0); break;
+        case SEG_G1_CORE: eval_exp_core_u32<2>(q, s.p0, s.p1, s.p2); break;
         case SEG_FLAGS: eval_flags(q, s.p0); break;
         case SEG_G1_ADD: eval_g1_add(q, q.lv(s.p1), s.p0); break;
         case SEG_G1_DOUBLE: eval_g1_double(q, q.lv(s.p1), s.p0); break;
