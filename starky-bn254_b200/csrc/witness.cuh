@@ -151,30 +151,35 @@ template <class W> HD bool g1_row(const u32* ax, const u32* ay, const u32* bx, c
 }
 
 // ---- Jacobian arithmetic for the exponentiation chain (y^2 = x^3 + 3, a = 0), Montgomery coordinates ----
+// The chain kernels run one warp per scheduler, so nothing hides instruction fetch: with every multiplication inlined
+// one add + double is ~150 KB of code, far beyond the instruction cache.  The formulas therefore call ONE out-of-line
+// copy of the Montgomery product.
+__host__ __device__ __noinline__ Fq fq_mul_call(const Fq& a, const Fq& b) { return fq_mul(a, b); }
 struct G1Jac { Fq x, y, z; };
+HD Fq fq_sqr_call(const Fq& a) { return fq_mul_call(a, a); }
 HD G1Jac g1_jac_dbl(const G1Jac& p) {
-  Fq A = fq_sqr(p.x), B = fq_sqr(p.y), C = fq_sqr(B);
+  Fq A = fq_sqr_call(p.x), B = fq_sqr_call(p.y), C = fq_sqr_call(B);
   Fq t = fq_add(p.x, B);
-  Fq D = fq_dbl(fq_sub(fq_sub(fq_sqr(t), A), C));
-  Fq E = fq_add(fq_dbl(A), A), Fv = fq_sqr(E);
+  Fq D = fq_dbl(fq_sub(fq_sub(fq_sqr_call(t), A), C));
+  Fq E = fq_add(fq_dbl(A), A), Fv = fq_sqr_call(E);
   G1Jac r;
   r.x = fq_sub(Fv, fq_dbl(D));
   Fq c8 = fq_dbl(fq_dbl(fq_dbl(C)));
-  r.y = fq_sub(fq_mul(E, fq_sub(D, r.x)), c8);
-  r.z = fq_dbl(fq_mul(p.y, p.z));
+  r.y = fq_sub(fq_mul_call(E, fq_sub(D, r.x)), c8);
+  r.z = fq_dbl(fq_mul_call(p.y, p.z));
   return r;
 }
 HD G1Jac g1_jac_add(const G1Jac& p, const G1Jac& q) {
-  Fq z1z1 = fq_sqr(p.z), z2z2 = fq_sqr(q.z);
-  Fq u1 = fq_mul(p.x, z2z2), u2 = fq_mul(q.x, z1z1);
-  Fq s1 = fq_mul(fq_mul(p.y, q.z), z2z2), s2 = fq_mul(fq_mul(q.y, p.z), z1z1);
+  Fq z1z1 = fq_sqr_call(p.z), z2z2 = fq_sqr_call(q.z);
+  Fq u1 = fq_mul_call(p.x, z2z2), u2 = fq_mul_call(q.x, z1z1);
+  Fq s1 = fq_mul_call(fq_mul_call(p.y, q.z), z2z2), s2 = fq_mul_call(fq_mul_call(q.y, p.z), z1z1);
   Fq h = fq_sub(u2, u1);
-  Fq i = fq_sqr(fq_dbl(h)), j = fq_mul(h, i);
-  Fq rr = fq_dbl(fq_sub(s2, s1)), v = fq_mul(u1, i);
+  Fq i = fq_sqr_call(fq_dbl(h)), j = fq_mul_call(h, i);
+  Fq rr = fq_dbl(fq_sub(s2, s1)), v = fq_mul_call(u1, i);
   G1Jac r;
-  r.x = fq_sub(fq_sub(fq_sqr(rr), j), fq_dbl(v));
-  r.y = fq_sub(fq_mul(rr, fq_sub(v, r.x)), fq_dbl(fq_mul(s1, j)));
-  r.z = fq_mul(fq_sub(fq_sub(fq_sqr(fq_add(p.z, q.z)), z1z1), z2z2), h);
+  r.x = fq_sub(fq_sub(fq_sqr_call(rr), j), fq_dbl(v));
+  r.y = fq_sub(fq_mul_call(rr, fq_sub(v, r.x)), fq_dbl(fq_mul_call(s1, j)));
+  r.z = fq_mul_call(fq_sub(fq_sub(fq_sqr_call(fq_add(p.z, q.z)), z1z1), z2z2), h);
   return r;
 }
 
@@ -215,12 +220,12 @@ HD Fq2 fq2_add(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = fq_add(a.c0, b.c0); r
 HD Fq2 fq2_sub(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = fq_sub(a.c0, b.c0); r.c1 = fq_sub(a.c1, b.c1); return r; }
 HD Fq2 fq2_dbl(const Fq2& a) { return fq2_add(a, a); }
 HD Fq2 fq2_mul(const Fq2& a, const Fq2& b) {   // Karatsuba: 3 base multiplications
-  Fq t0 = fq_mul(a.c0, b.c0), t1 = fq_mul(a.c1, b.c1);
-  Fq s = fq_mul(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+  Fq t0 = fq_mul_call(a.c0, b.c0), t1 = fq_mul_call(a.c1, b.c1);
+  Fq s = fq_mul_call(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
   Fq2 r; r.c0 = fq_sub(t0, t1); r.c1 = fq_sub(fq_sub(s, t0), t1); return r;
 }
 HD Fq2 fq2_sqr(const Fq2& a) {   // (c0 + c1)(c0 - c1), 2 c0 c1
-  Fq2 r; r.c0 = fq_mul(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1)); r.c1 = fq_dbl(fq_mul(a.c0, a.c1)); return r;
+  Fq2 r; r.c0 = fq_mul_call(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1)); r.c1 = fq_dbl(fq_mul_call(a.c0, a.c1)); return r;
 }
 HD bool fq2_is_zero(const Fq2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
 HD Fq2 fq2_inv(const Fq2& a) {   // conj(a) / (c0^2 + c1^2)
@@ -364,8 +369,8 @@ HD Fq fq12_mul_coeff(const Fq* x, const Fq* y, int oi) {
     for (int i = 0; i < 6; i++) {
       const int j = m - i;
       if (j < 0 || j > 5) continue;
-      if (part == 0) sum = fq_sub(fq_add(sum, fq_mul(x[i], y[j])), fq_mul(x[i + 6], y[j + 6]));
-      else sum = fq_add(fq_add(sum, fq_mul(x[i], y[j + 6])), fq_mul(x[i + 6], y[j]));
+      if (part == 0) sum = fq_sub(fq_add(sum, fq_mul_call(x[i], y[j])), fq_mul_call(x[i + 6], y[j + 6]));
+      else sum = fq_add(fq_add(sum, fq_mul_call(x[i], y[j + 6])), fq_mul_call(x[i + 6], y[j]));
     }
     if (wgt == 9) { Fq s2 = fq_dbl(sum), s4 = fq_dbl(s2), s8 = fq_dbl(s4); sum = fq_add(s8, sum); }
     acc = wgt < 0 ? fq_sub(acc, sum) : fq_add(acc, sum);
