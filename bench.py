@@ -82,7 +82,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core (rank 0 alone runs it)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     orc = entry.load_oracle()
+    orc.set_threads(os.cpu_count())
     sbn = entry.load_package()
     ios = getattr(sbn.synthetic, AIRS[AIR][3])(NUM_IO)
     cores = os.cpu_count()
@@ -115,7 +118,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--air", default="g1", choices=sorted(AIRS))
-    ap.add_argument("--inflight", type=int, default=3, help="independent proofs in flight per GPU (one context + CUDA stream each)")
+    ap.add_argument("--inflight", type=int, default=4, help="independent proofs in flight per GPU (one context + CUDA stream each)")
     args = ap.parse_args()
     select_air(args.air)
     if args.impl == "reference":
@@ -286,17 +289,26 @@ def main():
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon Merkle leaves)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None,
+                     # ncu --set full capture of the trace-commitment launch (profiles/r01_leaf_hash_ncu_summary_l22.txt): dram read + write
+                     # 1.7619 GB + 8.75 MB = its algorithmic bytes (1676 columns x 2^17 rows x 8 B + digests): no re-reads.  G1 shape only.
+                     "traffic": 1.7706e9 if AIR == "g1" else None,
+                     "traffic_note": "largest of the 3 launches per proof (trace commitment); `achieved` averages all 3 (trace, Z, quotient commitments)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                      "note": "kernel is INT-pipe bound (Poseidon ~ 2e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
                      "share_of_kernel_time": leaf["ms"] / total_kernel_ms if total_kernel_ms else None},
-        "int_pipe": {"poseidon_perms_per_s": perms_per_proof * ksteps / (leaf["ms"] / 1e3) if leaf["ms"] else None, "perms_per_proof": perms_per_proof},
+        # integer-issue view of the same kernel: ncu counts 29.3k thread instructions per permutation for this build
+        # (25.25 G warp instructions / 27.5 M permutations x 32); peak = 148 SMs x 4 schedulers x 1 instr/clk x sm_max_mhz
+        "int_pipe": {"poseidon_perms_per_s": perms_per_proof * ksteps / (leaf["ms"] / 1e3) if leaf["ms"] else None, "perms_per_proof": perms_per_proof,
+                     "warp_instr_per_perm": 29.3e3 / 32,
+                     "issue_frac": (perms_per_proof * ksteps / (leaf["ms"] / 1e3) * 29.3e3 / 32) / (148 * 4 * 1965e6) if leaf["ms"] else None},
         "serial_ms_per_step": serial_ms_per_step,
         "kernel_ms_per_proof": {k: round(v["ms"] / ksteps, 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
         "phase_ms_last_proof": {k: round(v, 3) for k, v in phases.items()},
     }
     if not args.no_cpu_baseline and world == 1:
         orc = entry.load_oracle()
+        orc.set_threads(os.cpu_count())
         full_ms, est, wall = cpu_sample(orc, gen_ios(NUM_IO))
         line["cpu_baseline"] = {"value": 1000.0 / full_ms, "unit": "proofs/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "oracle (C++/OpenMP restatement, not the Rust binary): heavy phases on 1/%d of their columns/instances/points scaled x%d, "

@@ -10,6 +10,7 @@
 #include "air_fq12.hpp"
 #include "sample.hpp"
 #include <cstdio>
+#include <omp.h>
 #include <cstdlib>
 #include <memory>
 #include <sstream>
@@ -42,6 +43,8 @@ static Fq12Words mk12(const u64* p) { Fq12Words w; for (int i = 0; i < 12; i++) 
 
 extern "C" {
 const char* orc_last_error() { return g_err.c_str(); }
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_max_threads() { return omp_get_max_threads(); }
 void orc_set_field_params(u64 gen, u64 pow2) { g_field.mult_generator = gen; g_field.pow2_generator = pow2; }
 void orc_poseidon_fast(u64* st) { GF s[12]; for (int i = 0; i < 12; i++) s[i] = GF(st[i]); poseidon_fast(s); for (int i = 0; i < 12; i++) st[i] = s[i].v; }
 void orc_poseidon(u64* st) { GF s[12]; for (int i = 0; i < 12; i++) s[i] = GF(st[i]); poseidon(s); for (int i = 0; i < 12; i++) st[i] = s[i].v; }

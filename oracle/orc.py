@@ -65,6 +65,11 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def set_threads(n):
+    """OpenMP thread count of the oracle (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
 def poseidon(state):
     s = np.ascontiguousarray(state, dtype=np.uint64).copy()
     lib().orc_poseidon(_p(s))
