@@ -90,19 +90,111 @@ __global__ void __launch_bounds__(32) k_lookup_walk(const u32* __restrict__ cnt_
   for (size_t k = lane; k < ndef; k += 32) perm[defer[k]] = k < top ? stack[k] : R - 1;
 }
 
+// Same algorithm, 32 table values per step: the warp loads 32 counts at once, replays their pushes and pops on
+// BIT MASKS in registers (only lanes with surplus copies are visited; a pop takes the highest still-available in-chunk
+// push, then entries of the global stack below the chunk), and then every lane writes its own run.  The sequential
+// kernel above spends one dependent global-memory round trip per table value; this one spends one per 32 values.
+// Long runs (> 32 copies of one value: default rows, skewed limbs) are written by the whole warp.  Bit-identical output.
+__global__ void __launch_bounds__(32) k_lookup_walk_chunked(const u32* __restrict__ cnt_all, u32 R, size_t N, u64* __restrict__ cols, const LookupDesc* __restrict__ descs,
+                                                            u32* __restrict__ stack_all, uint2* __restrict__ defer_all) {
+  const int lane = threadIdx.x;
+  const LookupDesc d = descs[blockIdx.x];
+  const u32* cnt = cnt_all + (size_t)blockIdx.x * R;
+  u32* stack = stack_all + (size_t)blockIdx.x * R;
+  uint2* defr = defer_all + (size_t)blockIdx.x * R;
+  u64* sorted = cols + (size_t)d.sorted_col * N;
+  u64* perm = cols + (size_t)d.perm_col * N;
+  u32 off = 0, top = 0, ndef = 0, last_off = 0;   // warp-uniform
+  u32 cnext = cnt[lane];
+  for (u32 v0 = 0; v0 < R; v0 += 32) {
+    const u32 v = v0 + lane;
+    const bool last = (v == R - 1);
+    const u32 c = cnext;
+    if (v0 + 32 < R) cnext = cnt[v + 32];          // prefetch the next chunk's counts
+    const u32 cs = last ? 1u : c;                  // the table's last value neither pushes nor pops
+    u32 incl = c;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, dd); if (lane >= dd) incl += t; }
+    const u32 myoff = off + incl - c;
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    const u32 zero_mask = __ballot_sync(0xffffffffu, cs == 0);
+    u32 pm = __ballot_sync(0xffffffffu, cs >= 2);
+    u32 consumed = 0, pre_top = top;
+    u32 my_taken = 0, my_pre_start = 0, my_pre_cnt = 0, my_def = 0, my_def_slot = 0;
+    while (pm) {
+      const int i = __ffs(pm) - 1;
+      pm &= pm - 1;
+      u32 dsur = __shfl_sync(0xffffffffu, cs, i) - 1;
+      u32 avail = zero_mask & ((1u << i) - 1) & ~consumed, taken = 0;
+      while (dsur > 0 && avail) { const int b = 31 - __clz(avail); avail ^= 1u << b; taken |= 1u << b; dsur--; }
+      consumed |= taken;
+      const u32 pre_take = dsur < pre_top ? dsur : pre_top;
+      if (lane == i) { my_taken = taken; my_pre_start = pre_top; my_pre_cnt = pre_take; my_def = dsur - pre_take; my_def_slot = ndef; }
+      pre_top -= pre_take;
+      if (dsur > pre_take) ndef++;
+    }
+    if (!last && c > 0) {
+      if (c <= 32) for (u32 t = 0; t < c; t++) sorted[myoff + t] = v;
+      perm[myoff] = v;
+      u32 p = myoff + 1;
+      for (u32 m = my_taken; m;) { const int b = 31 - __clz(m); m ^= 1u << b; perm[p++] = v0 + b; }
+      if (my_pre_cnt <= 32) for (u32 t = 0; t < my_pre_cnt; t++) perm[p + t] = stack[my_pre_start - 1 - t];
+      if (my_def) defr[my_def_slot] = make_uint2(p + my_pre_cnt, my_def);
+    }
+    u32 big = __ballot_sync(0xffffffffu, !last && (c > 32 || my_pre_cnt > 32));
+    while (big) {
+      const int i = __ffs(big) - 1;
+      big &= big - 1;
+      const u32 ci = __shfl_sync(0xffffffffu, c, i), oi = __shfl_sync(0xffffffffu, myoff, i);
+      if (ci > 32) for (u32 t = lane; t < ci; t += 32) sorted[oi + t] = v0 + i;
+      const u32 pc = __shfl_sync(0xffffffffu, my_pre_cnt, i), ps = __shfl_sync(0xffffffffu, my_pre_start, i);
+      const u32 pp = oi + 1 + __popc(__shfl_sync(0xffffffffu, my_taken, i));
+      if (pc > 32) for (u32 t = lane; t < pc; t += 32) perm[pp + t] = stack[ps - 1 - t];
+    }
+    __syncwarp();   // pops above read stack slots that the surviving pushes below may overwrite
+    const u32 surv = zero_mask & ~consumed;
+    if ((surv >> lane) & 1) stack[pre_top + __popc(surv & ((1u << lane) - 1))] = v;
+    top = pre_top + __popc(surv);
+    if (v0 + 32 >= R) last_off = __shfl_sync(0xffffffffu, myoff, 31);
+    off += total;
+    __syncwarp();
+  }
+  {  // v = R-1: the table holds tcount copies; surplus inputs are deferred, never popped (lookup.rs:79,103-104)
+    const size_t c = cnt[R - 1], tcount = N - R + 1, m = c < tcount ? c : tcount;
+    for (size_t t = lane; t < c; t += 32) sorted[last_off + t] = R - 1;
+    for (size_t t = lane; t < m; t += 32) perm[last_off + t] = R - 1;
+    if (c > tcount) { if (lane == 0) defr[ndef] = make_uint2((u32)(last_off + tcount), (u32)(c - tcount)); ndef++; }
+  }
+  __syncwarp();
+  // deferred positions (ascending) take the leftover unused values bottom-first, then the table's last value
+  u32 k = 0;
+  for (u32 j = 0; j < ndef; j++) {
+    const uint2 r = defr[j];
+    for (u32 t = lane; t < r.y; t += 32) perm[r.x + t] = (k + t < top) ? stack[k + t] : R - 1;
+    k += r.y;
+  }
+}
+
 static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::vector<LookupDesc>& descs) {
   SBN_REQUIRE(N >= R, "range-check table does not fit the trace (reference asserts rows >= range_max)");
   SBN_REQUIRE(N < (size_t(1) << 32), "trace too long");
+  SBN_REQUIRE(R % 32 == 0, "lookup table size must be a multiple of 32");
   DevBuf<int> err(ctx, 1);
   CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
-  // lookups are processed in groups so the scratch (stack + deferred list per lookup) stays bounded
-  size_t per = (N + R) * 4 + (size_t)R * 4;
+  // lookups are processed in groups so the scratch (counts, unused stack, deferred ranges per lookup) stays bounded
+  size_t per = (size_t)R * (4 + 4 + 8);
   size_t group = std::max<size_t>(1, (size_t(512) << 20) / per);
   group = std::min(group, descs.size());
   DevBuf<LookupDesc> d_desc(ctx, descs.size());
   CUDA_CHECK(cudaMemcpyAsync(d_desc, descs.data(), descs.size() * sizeof(LookupDesc), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  DevBuf<u32> cnt(ctx, group * R), stack(ctx, group * R), defer(ctx, group * N);
+  // SBN_LOOKUP_SEQUENTIAL=1 selects the one-value-per-step kernel (k_lookup_walk), kept as the in-library cross-check of the
+  // chunked kernel (tests/test_gpu_parity.py compares the two on skewed and uniform columns).
+  const bool sequential = getenv("SBN_LOOKUP_SEQUENTIAL") != nullptr;
+  if (sequential) group = std::min(group, std::max<size_t>(1, (size_t(512) << 20) / ((N + 2 * (size_t)R) * 4)));
+  DevBuf<u32> cnt(ctx, group * R), stack(ctx, group * R);
+  DevBuf<uint2> defer(ctx, sequential ? 1 : group * R);
+  DevBuf<u32> defer_seq(ctx, sequential ? group * N : 1);
   for (size_t g0 = 0; g0 < descs.size(); g0 += group) {
     size_t ng = std::min(group, descs.size() - g0);
     CUDA_CHECK(cudaMemsetAsync(cnt, 0, ng * R * 4, ctx->stream));
@@ -111,7 +203,8 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
     k_lookup_hist<<<dim3(bx, (unsigned)ng), 256, 0, ctx->stream>>>(d_cols, N, R, d_desc + g0, cnt, err);
     LAUNCH_CHECK(ctx); }
     KScope ks2(ctx, "lookup_walk");
-    k_lookup_walk<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer);
+    if (sequential) k_lookup_walk<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer_seq);
+    else k_lookup_walk_chunked<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer);
     LAUNCH_CHECK(ctx);
   }
   int h_err = 0;

@@ -90,6 +90,27 @@ def test_modular_trace_skewed_lookups(ctx, sbn, orc):
     assert (got == want).all()
 
 
+def test_lookup_kernels_agree(ctx, sbn, monkeypatch):
+    """The chunked lookup-walk kernel against the one-value-per-step kernel kept in the library as its cross-check: u16 table
+    (G1 trace, uniform and default-row-skewed columns) and split u8 table (ModularStark, all-equal and two-valued inputs)."""
+    g1 = sbn.G1ExpStark(128, ctx)
+    ios = sbn.synthetic.g1_exp_ios(128, seed=31)
+    a = g1.generate_trace(ios).download()
+    monkeypatch.setenv("SBN_LOOKUP_SEQUENTIAL", "1")
+    b = g1.generate_trace(ios).download()
+    monkeypatch.delenv("SBN_LOOKUP_SEQUENTIAL")
+    assert (a == b).all()
+    q = sbn.synthetic.BN254_P
+    n = 2048
+    rows = [(0, 0)] * 700 + [(q - 1, q - 1)] * 700 + [(1, q - 1)] * 648
+    mios = b"".join(x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in rows)
+    m = sbn.ModularStark(n, ctx)
+    a = m.generate_trace(mios).download()
+    monkeypatch.setenv("SBN_LOOKUP_SEQUENTIAL", "1")
+    b = m.generate_trace(mios).download()
+    assert (a == b).all()
+
+
 def test_modular_proof_matches_oracle_bytes(ctx, sbn, orc, golden, monkeypatch):
     monkeypatch.setenv("SBN_DEBUG_INTERMEDIATES", "1")
     n = 512
