@@ -18,14 +18,14 @@ __global__ void k_ext_powers(u64* out_a, u64* out_b, gl2 base, size_t n) {
 __global__ void __launch_bounds__(256) k_eval_two_points(const u64* __restrict__ coeffs, size_t N, const u64* __restrict__ pw /* [4][N]: z.a z.b zn.a zn.b */,
                                                          u64* __restrict__ out) {
   const u64* col = coeffs + (size_t)blockIdx.x * N;
-  u64 s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  gl_acc a0 = gl_acc_zero(), a1 = gl_acc_zero(), a2 = gl_acc_zero(), a3 = gl_acc_zero();   // unreduced sums of products
   for (size_t j = threadIdx.x; j < N; j += blockDim.x) {
     u64 c = col[j];
-    s0 = gl_add(s0, gl_mul(c, pw[j])); s1 = gl_add(s1, gl_mul(c, pw[N + j]));
-    s2 = gl_add(s2, gl_mul(c, pw[2 * N + j])); s3 = gl_add(s3, gl_mul(c, pw[3 * N + j]));
+    gl_acc_mac(a0, c, pw[j]); gl_acc_mac(a1, c, pw[N + j]);
+    gl_acc_mac(a2, c, pw[2 * N + j]); gl_acc_mac(a3, c, pw[3 * N + j]);
   }
   __shared__ u64 red[4][256];
-  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2; red[3][threadIdx.x] = s3;
+  red[0][threadIdx.x] = gl_acc_reduce(a0); red[1][threadIdx.x] = gl_acc_reduce(a1); red[2][threadIdx.x] = gl_acc_reduce(a2); red[3][threadIdx.x] = gl_acc_reduce(a3);
   __syncthreads();
   for (int d = 128; d > 0; d >>= 1) {
     if ((int)threadIdx.x < d) for (int k = 0; k < 4; k++) red[k][threadIdx.x] = gl_add(red[k][threadIdx.x], red[k][threadIdx.x + d]);

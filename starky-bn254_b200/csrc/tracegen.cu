@@ -542,30 +542,37 @@ HD bool fq12_exp_bit(const void* io_base, size_t io_size, size_t inst, int k, bo
   if (u64_variant) return (*(const u64*)p >> k) & 1;
   return (((const u32*)p)[k >> 5] >> (k & 31)) & 1;
 }
-// One block per instance, 24 threads: threads 0..11 square A, threads 12..23 multiply B by A when the bit is set.
+// One block per instance, 288 threads.  Per bit: thread (which, i, j) forms one pairwise product (which = 0: A_i A_j for the
+// squaring, 1: B_i A_j for the multiplication, skipped when the bit is clear); 24 threads sum the 144 products of their
+// output coefficient while 24 threads of another warp convert the current A, B to canonical words and store them.
 // chain[inst][2][nbits+1][12][8]: canonical words of A[k] = x^(2^k) and B[k] = offset * prod_{j<k, bit_j} A[j].
-__global__ void __launch_bounds__(32) k_fq12_chain(const void* __restrict__ ios, size_t io_size, int nbits, bool u64_variant, u32* __restrict__ chain, int* __restrict__ err) {
-  __shared__ Fq sa[2][12], sb[2][12];
+__global__ void __launch_bounds__(288) k_fq12_chain(const void* __restrict__ ios, size_t io_size, int nbits, bool u64_variant, u32* __restrict__ chain, int* __restrict__ err) {
+  __shared__ Fq sa[12], sb[12], pr[2][144];
   const size_t inst = blockIdx.x;
-  const int t = threadIdx.x, oi = t % 12, which = t / 12;
+  const int t = threadIdx.x, which = t / 144, ij = t % 144, pi = ij / 12, pj = ij % 12;
   const Fq12Io* io = (const Fq12Io*)((const unsigned char*)ios + inst * io_size);
   if (t < 24) {
     u32 w[8];
-    u64x4_to_words((which ? io->offset : io->x) + 4 * oi, w);
+    u64x4_to_words((const u64*)(t < 12 ? io->x : io->offset) + 4 * (t % 12), w);
     if (fq_geq_p(w)) *err = 2;
-    (which ? sb : sa)[0][oi] = fq_from_words(w);
+    (t < 12 ? sa : sb)[t % 12] = fq_from_words(w);
   }
   __syncthreads();
   u32* ca = chain + inst * 2 * (size_t)(nbits + 1) * 96; u32* cb = ca + (size_t)(nbits + 1) * 96;
   for (int k = 0; k <= nbits; k++) {
-    const int cur = k & 1, nxt = cur ^ 1;
-    if (t < 24) {
-      fq_to_words((which ? sb : sa)[cur][oi], (which ? cb : ca) + ((size_t)k * 12 + oi) * 8);
-      if (k < nbits) {
-        if (which == 0) sa[nxt][oi] = fq12_mul_coeff(sa[cur], sa[cur], oi);
-        else sb[nxt][oi] = fq12_exp_bit(ios, io_size, inst, k, u64_variant) ? fq12_mul_coeff(sb[cur], sa[cur], oi) : sb[cur][oi];
-      }
+    const bool bit = k < nbits && fq12_exp_bit(ios, io_size, inst, k, u64_variant);
+    if (k < nbits && (which == 0 || bit)) pr[which][ij] = fq_mul((which ? sb : sa)[pi], sa[pj]);
+    if (t >= 32 && t < 56) {   // canonical words of the current values (a separate warp from the summing threads)
+      const int c = t - 32;
+      fq_to_words((c < 12 ? sa : sb)[c % 12], (c < 12 ? ca : cb) + ((size_t)k * 12 + c % 12) * 8);
     }
+    if (k == nbits) break;
+    __syncthreads();
+    Fq nv;
+    if (t < 12) nv = fq12_sum_coeff(pr[0], t);
+    else if (t < 24 && bit) nv = fq12_sum_coeff(pr[1], t - 12);
+    __syncthreads();
+    if (t < 12) sa[t] = nv; else if (t < 24 && bit) sb[t - 12] = nv;
     __syncthreads();
   }
 }
@@ -631,7 +638,7 @@ static void generate_fq12(sbn_ctx* ctx, const AirDesc& air, const void* ios, boo
   CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
   const size_t per_inst = (size_t)2 * (nbits + 1) * 96;
   DevBuf<u32> chain(ctx, n * per_inst);
-  { KScope ks(ctx, "fq12_chain"); k_fq12_chain<<<(unsigned)n, 32, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, err); LAUNCH_CHECK(ctx); }
+  { KScope ks(ctx, "fq12_chain"); k_fq12_chain<<<(unsigned)n, 288, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, err); LAUNCH_CHECK(ctx); }
   { KScope ks(ctx, "fq12_rows"); k_fq12_rows<<<(unsigned)(N / 32), 384, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, d_cols, N); LAUNCH_CHECK(ctx); }
   std::vector<u32> res(n * 96);
   for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 96, chain + i * per_inst + (size_t)(nbits + 1) * 96 + (size_t)nbits * 96, 384, cudaMemcpyDeviceToHost, ctx->stream));

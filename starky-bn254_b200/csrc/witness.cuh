@@ -377,6 +377,29 @@ HD Fq fq12_mul_coeff(const Fq* x, const Fq* y, int oi) {
   }
   return acc;
 }
+// Same coefficient from the 144 pairwise products prod[12 * i + j] = x_i * y_j (the chain kernel computes those with one
+// thread each and sums them here).
+HD Fq fq12_sum_coeff(const Fq* prod, int oi) {
+  const bool imag = oi >= 6; const int i0 = imag ? oi - 6 : oi;
+  Fq acc = fq_zero();
+  for (int term = 0; term < 3; term++) {
+    int m, part, wgt;
+    if (term == 0) { m = i0; part = imag ? 1 : 0; wgt = 1; }
+    else if (i0 == 5) break;
+    else if (term == 1) { m = i0 + 6; part = 0; wgt = imag ? 1 : 9; }
+    else { m = i0 + 6; part = 1; wgt = imag ? 9 : -1; }
+    Fq sum = fq_zero();
+    for (int i = 0; i < 6; i++) {
+      const int j = m - i;
+      if (j < 0 || j > 5) continue;
+      if (part == 0) sum = fq_sub(fq_add(sum, prod[12 * i + j]), prod[12 * (i + 6) + j + 6]);
+      else sum = fq_add(fq_add(sum, prod[12 * i + j + 6]), prod[12 * (i + 6) + j]);
+    }
+    if (wgt == 9) { Fq s2 = fq_dbl(sum), s4 = fq_dbl(s2), s8 = fq_dbl(s4); sum = fq_add(s8, sum); }
+    acc = wgt < 0 ? fq_sub(acc, sum) : fq_add(acc, sum);
+  }
+  return acc;
+}
 // i64 limb polynomial of output coefficient `oi` of pol_mul_fq12(x, y, 9); xl / yl: 12 x 16 limbs (u16 values)
 HD void fq12_pol_input(const unsigned short* xl, const unsigned short* yl, int oi, i64* pol /*31*/) {
   for (int k = 0; k < 31; k++) pol[k] = 0;

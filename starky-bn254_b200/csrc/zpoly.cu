@@ -24,8 +24,10 @@ __device__ __forceinline__ void row_num_den(const u64* __restrict__ trace, size_
     den = gl_mul(den, gl_add(trace[(size_t)rhs[e] * stride + r], g));
   }
 }
-// block-wide inclusive multiplicative scans: prefix over v (result in pre) and suffix over w (result in suf)
-__device__ __forceinline__ void block_scan_mul(u64 v, u64 w, u64& pre, u64& suf, u64& total_v, u64& total_w) {
+// block-wide inclusive multiplicative scans: prefix over v (result in pre) and suffix over w (result in suf).
+// Warp scans by shuffle; the 8 warp totals are scanned once by warp 0 and shared, so a thread pays 10 multiplications for
+// the warp level and 2 for the block level.
+__device__ __forceinline__ void block_scan_mul(u64 v, u64 w, u64& pre, u64& suf) {
   __shared__ u64 sv[ZT / 32], sw[ZT / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u64 a = v, b = w;
@@ -37,15 +39,30 @@ __device__ __forceinline__ void block_scan_mul(u64 v, u64 w, u64& pre, u64& suf,
   if (lane == 31) sv[warp] = a;
   if (lane == 0) sw[warp] = b;
   __syncthreads();
-  u64 pa = 1, sb = 1, tv = 1, tw = 1;
-  for (int i = 0; i < ZT / 32; i++) {
-    u64 x = sv[i], y = sw[i];
-    if (i < warp) pa = gl_mul(pa, x);
-    if (i > warp) sb = gl_mul(sb, y);
-    tv = gl_mul(tv, x); tw = gl_mul(tw, y);
+  if (warp == 0) {   // exclusive prefix of the warp totals of v, exclusive suffix of those of w
+    u64 x = lane < ZT / 32 ? sv[lane] : 1, y = lane < ZT / 32 ? sw[lane] : 1;
+    u64 px = x, sy = y;
+    for (int d = 1; d < ZT / 32; d <<= 1) {
+      u64 tx = __shfl_up_sync(0xffffffffu, px, d), ty = __shfl_down_sync(0xffffffffu, sy, d);
+      if (lane >= d) px = gl_mul(px, tx);
+      if (lane + d < ZT / 32) sy = gl_mul(sy, ty);
+    }
+    u64 ex = __shfl_up_sync(0xffffffffu, px, 1), ey = __shfl_down_sync(0xffffffffu, sy, 1);
+    if (lane < ZT / 32) { sv[lane] = lane == 0 ? 1 : ex; sw[lane] = lane == ZT / 32 - 1 ? 1 : ey; }
   }
-  pre = gl_mul(a, pa); suf = gl_mul(b, sb); total_v = tv; total_w = tw;
   __syncthreads();
+  pre = gl_mul(a, sv[warp]); suf = gl_mul(b, sw[warp]);
+  __syncthreads();
+}
+// block-wide products of v and of w (valid in thread 0)
+__device__ __forceinline__ void block_reduce_mul(u64 v, u64 w, u64& tv, u64& tw) {
+  __shared__ u64 rv[ZT / 32], rw[ZT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = 16; d >= 1; d >>= 1) { v = gl_mul(v, __shfl_xor_sync(0xffffffffu, v, d)); w = gl_mul(w, __shfl_xor_sync(0xffffffffu, w, d)); }
+  if (lane == 0) { rv[warp] = v; rw[warp] = w; }
+  __syncthreads();
+  tv = 1; tw = 1;
+  if (threadIdx.x == 0) for (int i = 0; i < ZT / 32; i++) { tv = gl_mul(tv, rv[i]); tw = gl_mul(tw, rw[i]); }
 }
 
 __global__ void __launch_bounds__(ZT) k_z_tile_products(const u64* __restrict__ trace, size_t stride, const u32* lhs, const u32* rhs, const u64* gamma,
@@ -54,8 +71,8 @@ __global__ void __launch_bounds__(ZT) k_z_tile_products(const u64* __restrict__ 
   size_t r = (size_t)tile * ZT + threadIdx.x;
   u64 num, den;
   row_num_den(trace, stride, r, lhs, rhs, gamma, batch, z, num, den);
-  u64 pre, suf, tn, td;
-  block_scan_mul(num, den, pre, suf, tn, td);
+  u64 tn, td;
+  block_reduce_mul(num, den, tn, td);
   if (threadIdx.x == 0) { tile_num[(size_t)z * ntiles + tile] = tn; tile_den[(size_t)z * ntiles + tile] = td; }
 }
 // per column: tile_num -> exclusive prefix, tile_den -> exclusive suffix times 1/prod(all den)
@@ -76,8 +93,8 @@ __global__ void __launch_bounds__(ZT) k_z_finish(const u64* __restrict__ trace, 
   size_t r = (size_t)tile * ZT + threadIdx.x;
   u64 num, den;
   row_num_den(trace, stride, r, lhs, rhs, gamma, batch, z, num, den);
-  u64 pre, suf, tn, td;
-  block_scan_mul(num, den, pre, suf, tn, td);
+  u64 pre, suf;
+  block_scan_mul(num, den, pre, suf);
   // exclusive prefix of num within the tile = inclusive prefix of the previous thread
   u64 pre_ex = __shfl_up_sync(0xffffffffu, pre, 1);
   __shared__ u64 warp_last[ZT / 32];

@@ -131,6 +131,13 @@ void emu_fq12_mul(const u32* x, const u32* y, u32* out) {
   for (int i = 0; i < 12; i++) { xm[i] = fq_from_words(x + 8 * i); ym[i] = fq_from_words(y + 8 * i); }
   for (int oi = 0; oi < 12; oi++) fq_to_words(fq12_mul_coeff(xm, ym, oi), out + 8 * oi);
 }
+// the same product the way k_fq12_chain forms it: 144 pairwise products, then fq12_sum_coeff per output coefficient
+void emu_fq12_mul_pairwise(const u32* x, const u32* y, u32* out) {
+  Fq xm[12], ym[12], pr[144];
+  for (int i = 0; i < 12; i++) { xm[i] = fq_from_words(x + 8 * i); ym[i] = fq_from_words(y + 8 * i); }
+  for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) pr[12 * i + j] = fq_mul(xm[i], ym[j]);
+  for (int oi = 0; oi < 12; oi++) fq_to_words(fq12_sum_coeff(pr, oi), out + 8 * oi);
+}
 // Fq12 main columns a,b,output (1728) of one row, written the way k_fq12_rows does (one coefficient at a time)
 void emu_fq12_row(const u32* a, const u32* b, const u32* out_words, int op, u64* row) {
   RowWriter w{row};

@@ -243,6 +243,9 @@ def test_fq12_rows_match_oracle(emu, orc, sbn, air_id, num_io, rows):
             got = np.zeros(96, dtype=np.uint32)
             emu.emu_fq12_mul(vp(a), vp(a if op == 2 else b), vp(got))
             assert (got == out).all(), r
+            got2 = np.zeros(96, dtype=np.uint32)
+            emu.emu_fq12_mul_pairwise(vp(a), vp(a if op == 2 else b), vp(got2))
+            assert (got2 == out).all(), r
         # flag columns
         if u64v:
             e = int.from_bytes(ios[(r // 128) * syn.FQ12_U64_IO_SIZE + 768:(r // 128) * syn.FQ12_U64_IO_SIZE + 776], "little")
