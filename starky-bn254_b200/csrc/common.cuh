@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 #include <stdexcept>
@@ -39,6 +40,7 @@ struct sbn_ctx {
   std::vector<Block> blocks;
   size_t bytes_allocated = 0;
   std::map<int, NttTables> ntt_tables;
+  std::map<std::tuple<int, bool, u64>, u64*> fourstep_tables;   // (logn, inverse, coset base) -> ntt.cu F table
   std::map<std::pair<u64, int>, u64*> pow_tables;  // (base, logn) -> base^i, i < 2^logn
   unsigned long long launches = 0;                 // kernels launched by this library (bench: gpu_launches)
   // optional per-kernel-family CUDA-event timing on ctx->stream (bench.py roofline + breakdown)

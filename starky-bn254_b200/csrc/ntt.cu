@@ -103,6 +103,14 @@ __device__ __forceinline__ void smem_ntt(u64* s, const u64* tw, int l, int logT)
     lp -= r;
   }
 }
+template <int L, int LP> __device__ __forceinline__ void smem_ntt_ct(u64* s, const u64* tw, int logT) {   // the same with L known
+  if constexpr (LP > 0) {
+    constexpr int r = LP >= 4 ? 4 : LP;
+    smem_pass<r>(s, tw, L, LP, logT);
+    __syncthreads();
+    smem_ntt_ct<L, LP - r>(s, tw, logT);
+  }
+}
 HD int ntt_pos_to_k(int pos, int l) {   // position in the tile after smem_ntt -> frequency index
   int k = 0, shift = 0, lp = l;
   while (lp > 0) {
@@ -113,64 +121,120 @@ HD int ntt_pos_to_k(int pos, int l) {   // position in the tile after smem_ntt -
   return k;
 }
 
-// Pass 1 of the four-step transform: for a tile of T consecutive n2, length-N1 NTT over n1
-// (elements N2 apart), then the inter-step twiddle w_N^(n2*k1).  in -> tmp, same [N2*k1 + n2] layout.
-__global__ void __launch_bounds__(256) k_ntt_pass1(const u64* __restrict__ in, size_t in_stride, u64* __restrict__ tmp, const u64* __restrict__ W,
-                                                   const u64* __restrict__ prescale, int l1, int l2, int logT) {
+// Four-step transform N = N1 * N2 (n = N2 n1 + n2, k = k1 + N1 k2) as two kernels, sub-transform size a template
+// parameter so that every loop has a compile-time trip count.  A block keeps 2^L x T elements in shared memory
+// (T = 2^LOGT columns of the N1 x N2 matrix); each thread moves its elements in batches of 8 independent loads.
+//   pass 1: tile of T consecutive n2: length-N1 transform over n1, then times F[k1][n2], in -> tmp (same [k1 N2 + n2] layout)
+//   pass 2: tile of T consecutive k1: length-N2 transform over n2 (contiguous), tmp -> X[k1 + N1 k2]
+// F[k1][n2] = w_N^(n2 k1) * c^n2 * scale carries the four-step twiddle, the n2 part of a coset shift c (evaluation on
+// c<w>: input times c^n, c^n = (c^N2)^n1 c^n2; the n1 part is the row factor P1[n1] applied on load) and the 1/N of an
+// inverse transform, so those cost no instructions; it is read with the same coalesced index the result is stored at.
+__host__ __device__ constexpr int ntt_logT_of(int l) { return 13 - l > 5 ? 5 : (13 - l < 0 ? 0 : 13 - l); }
+constexpr int NTT_THREADS = 256, NTT_BATCH = 8;
+
+template <int L1, bool PRE> __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass1(const u64* __restrict__ in, size_t in_stride, u64* __restrict__ tmp,
+    const u64* __restrict__ W, const u64* __restrict__ F, const u64* __restrict__ P1, int l2) {
   extern __shared__ u64 smem[];
-  const int N1 = 1 << l1, T = 1 << logT, TS = ntt_row_stride(logT);
-  const size_t N = size_t(1) << (l1 + l2);
+  constexpr int LOGT = ntt_logT_of(L1), N1 = 1 << L1, T = 1 << LOGT, TS = T + (LOGT > 0 ? 1 : 0), TOTAL = N1 << LOGT;
+  static_assert(TOTAL % (NTT_THREADS * NTT_BATCH) == 0, "tile is a whole number of load batches");
+  const size_t N = size_t(1) << (L1 + l2);
   u64* s = smem;
   u64* tw = smem + (size_t)N1 * TS;
-  const u64* src = in + (size_t)blockIdx.y * in_stride;
-  u64* dst = tmp + (size_t)blockIdx.y * N;
-  const int n2_0 = blockIdx.x << logT;
-  for (int j = threadIdx.x; j < N1; j += blockDim.x) tw[j] = W[(size_t)j << l2];
-  for (int idx = threadIdx.x; idx < (N1 << logT); idx += blockDim.x) {
-    int n1 = idx >> logT, t = idx & (T - 1);
-    size_t n = ((size_t)n1 << l2) + n2_0 + t;
-    u64 v = src[n];
-    if (prescale) v = gl_mul_nc(v, prescale[n]);
-    s[n1 * TS + t] = v;
+  const u64* src = in + (size_t)blockIdx.y * in_stride + ((size_t)blockIdx.x << LOGT);
+  u64* dst = tmp + (size_t)blockIdx.y * N + ((size_t)blockIdx.x << LOGT);
+  const u64* Fb = F + ((size_t)blockIdx.x << LOGT);
+  for (int j = threadIdx.x; j < N1; j += NTT_THREADS) tw[j] = W[(size_t)j << l2];
+#pragma unroll 1
+  for (int base = threadIdx.x; base < TOTAL; base += NTT_THREADS * NTT_BATCH) {
+    u64 v[NTT_BATCH], pf[NTT_BATCH];
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) {
+      const int idx = base + u * NTT_THREADS, n1 = idx >> LOGT, t = idx & (T - 1);
+      v[u] = src[((size_t)n1 << l2) + t];
+      if (PRE) pf[u] = P1[n1];
+    }
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) {
+      const int idx = base + u * NTT_THREADS, n1 = idx >> LOGT, t = idx & (T - 1);
+      s[n1 * TS + t] = PRE ? gl_mul_nc(v[u], pf[u]) : v[u];
+    }
   }
   __syncthreads();
-  smem_ntt(s, tw, l1, logT);
-  for (int idx = threadIdx.x; idx < (N1 << logT); idx += blockDim.x) {
-    int pos = idx >> logT, t = idx & (T - 1);
-    int k1 = ntt_pos_to_k(pos, l1);
-    size_t n2 = n2_0 + t;
-    u64 v = gl_mul_nc(s[pos * TS + t], W[n2 * k1]);
-    dst[((size_t)k1 << l2) + n2] = v;     // lazy representative: pass 2 reduces it again
+  smem_ntt_ct<L1, L1>(s, tw, LOGT);
+#pragma unroll 1
+  for (int base = threadIdx.x; base < TOTAL; base += NTT_THREADS * NTT_BATCH) {
+    u64 f[NTT_BATCH];
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) {
+      const int idx = base + u * NTT_THREADS, pos = idx >> LOGT, t = idx & (T - 1);
+      f[u] = Fb[((size_t)ntt_pos_to_k(pos, L1) << l2) + t];
+    }
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) {
+      const int idx = base + u * NTT_THREADS, pos = idx >> LOGT, t = idx & (T - 1);
+      dst[((size_t)ntt_pos_to_k(pos, L1) << l2) + t] = gl_mul_nc(s[pos * TS + t], f[u]);   // lazy representative: pass 2 reduces it again
+    }
   }
 }
 
-// Pass 2: for a tile of T consecutive k1, length-N2 NTT over n2 (contiguous), output X[k1 + N1*k2].
-__global__ void __launch_bounds__(256) k_ntt_pass2(const u64* __restrict__ tmp, u64* __restrict__ out, size_t out_stride, const u64* __restrict__ W,
-                                                   const u64* __restrict__ postscale, u64 scale, int l1, int l2, int logT) {
+template <int L2> __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass2(const u64* __restrict__ tmp, u64* __restrict__ out, size_t out_stride,
+    const u64* __restrict__ W, const u64* __restrict__ postscale, int l1) {
   extern __shared__ u64 smem[];
-  const int N2 = 1 << l2, T = 1 << logT, TS = ntt_row_stride(logT);
-  const size_t N = size_t(1) << (l1 + l2);
+  constexpr int LOGT = ntt_logT_of(L2), N2 = 1 << L2, T = 1 << LOGT, TS = T + (LOGT > 0 ? 1 : 0), TOTAL = N2 << LOGT;
+  static_assert(TOTAL % (NTT_THREADS * NTT_BATCH) == 0, "tile is a whole number of load batches");
+  const size_t N = size_t(1) << (l1 + L2);
   u64* s = smem;
   u64* tw = smem + (size_t)N2 * TS;
-  const u64* src = tmp + (size_t)blockIdx.y * N;
-  u64* dst = out + (size_t)blockIdx.y * out_stride;
-  const int k1_0 = blockIdx.x << logT;
-  for (int j = threadIdx.x; j < N2; j += blockDim.x) tw[j] = W[(size_t)j << l1];
-  for (int idx = threadIdx.x; idx < (N2 << logT); idx += blockDim.x) {
-    int t = idx >> l2, n2 = idx & (N2 - 1);
-    s[n2 * TS + t] = src[((size_t)(k1_0 + t) << l2) + n2];
+  const size_t k1_0 = (size_t)blockIdx.x << LOGT;
+  const u64* src = tmp + (size_t)blockIdx.y * N + (k1_0 << L2);
+  u64* dst = out + (size_t)blockIdx.y * out_stride + k1_0;
+  for (int j = threadIdx.x; j < N2; j += NTT_THREADS) tw[j] = W[(size_t)j << l1];
+#pragma unroll 1
+  for (int base = threadIdx.x; base < TOTAL; base += NTT_THREADS * NTT_BATCH) {
+    u64 v[NTT_BATCH];
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) v[u] = src[base + u * NTT_THREADS];        // the T rows of the tile are one contiguous run
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) {
+      const int idx = base + u * NTT_THREADS, t = idx >> L2, n2 = idx & (N2 - 1);
+      s[n2 * TS + t] = v[u];
+    }
   }
   __syncthreads();
-  smem_ntt(s, tw, l2, logT);
-  for (int idx = threadIdx.x; idx < (N2 << logT); idx += blockDim.x) {
-    int pos = idx >> logT, t = idx & (T - 1);
-    int k2 = ntt_pos_to_k(pos, l2);
-    size_t k = (size_t)k1_0 + t + ((size_t)k2 << l1);
-    u64 v = s[pos * TS + t];
-    if (scale != 1) v = gl_mul_nc(v, scale);
-    if (postscale) v = gl_mul_nc(v, postscale[k]);
-    dst[k] = gl_canon(v);
+  smem_ntt_ct<L2, L2>(s, tw, LOGT);
+  const bool post = postscale != nullptr;
+#pragma unroll 1
+  for (int base = threadIdx.x; base < TOTAL; base += NTT_THREADS * NTT_BATCH) {
+#pragma unroll
+    for (int u = 0; u < NTT_BATCH; u++) {
+      const int idx = base + u * NTT_THREADS, pos = idx >> LOGT, t = idx & (T - 1);
+      const size_t k = ((size_t)ntt_pos_to_k(pos, L2) << l1) + t;
+      u64 v = s[pos * TS + t];
+      if (post) v = gl_mul_nc(v, postscale[k1_0 + k]);
+      dst[k] = gl_canon(v);
+    }
   }
+}
+__global__ void k_fourstep_table(u64* __restrict__ out, u64 w, u64 c, u64 scale, int l2, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 k1 = i >> l2, n2 = i & ((size_t(1) << l2) - 1);
+  out[i] = gl_mul(gl_mul(gl_pow(w, n2 * k1), gl_pow(c, n2)), scale);
+}
+// (logn, inverse, coset base) -> F table (device, N entries), built once per context
+static const u64* get_fourstep_table(sbn_ctx* ctx, int logn, bool inverse, u64 c) {
+  auto key = std::make_tuple(logn, inverse, c);
+  auto it = ctx->fourstep_tables.find(key);
+  if (it != ctx->fourstep_tables.end()) return it->second;
+  const size_t n = size_t(1) << logn;
+  const int l1 = logn / 2, l2 = logn - l1;
+  u64 w = gl_root_of_unity(logn);
+  if (inverse) w = gl_inv(w);
+  u64* p; CUDA_CHECK(cudaMalloc(&p, n * 8));
+  k_fourstep_table<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, w, c ? c : 1, inverse ? gl_inv((u64)n) : 1, l2, n);
+  LAUNCH_CHECK(ctx);
+  ctx->fourstep_tables[key] = p;
+  return p;
 }
 
 // Whole transform in one block (N <= 2048): one column per block.
@@ -200,23 +264,45 @@ __global__ void k_ntt_small(const u64* __restrict__ in, size_t in_stride, u64* _
   }
 }
 
-static int pick_logT(int l) {
-  // tile = 2^l * T * 8 bytes <= 64 KiB, T <= 32
-  int logT = 13 - l;
-  if (logT > 5) logT = 5;
-  if (logT < 0) logT = 0;
-  return logT;
+template <int L> static void launch_pass1(sbn_ctx* ctx, dim3 grid, size_t smem, bool pre, const u64* in, size_t in_stride, u64* tmp, const u64* W, const u64* F, const u64* P1, int l2) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  if (pre) k_ntt_pass1<L, true><<<grid, NTT_THREADS, smem, ctx->stream>>>(in, in_stride, tmp, W, F, P1, l2);
+  else k_ntt_pass1<L, false><<<grid, NTT_THREADS, smem, ctx->stream>>>(in, in_stride, tmp, W, F, P1, l2);
 }
+template <int L> static void launch_pass2(sbn_ctx* ctx, dim3 grid, size_t smem, const u64* tmp, u64* out, size_t out_stride, const u64* W, const u64* postscale, int l1) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  k_ntt_pass2<L><<<grid, NTT_THREADS, smem, ctx->stream>>>(tmp, out, out_stride, W, postscale, l1);
+}
+#define NTT_DISPATCH_L(l, CALL) \
+  switch (l) { case 6: { constexpr int L = 6; CALL; } break; case 7: { constexpr int L = 7; CALL; } break; case 8: { constexpr int L = 8; CALL; } break; \
+    case 9: { constexpr int L = 9; CALL; } break; case 10: { constexpr int L = 10; CALL; } break; case 11: { constexpr int L = 11; CALL; } break; \
+    case 12: { constexpr int L = 12; CALL; } break; default: SBN_REQUIRE(false, "ntt: unsupported sub-transform size"); }
 
+// Transform of `ncols` columns.  pre_base c != 0: evaluate on the coset c<w> (input times c^n); postscale: optional table
+// the output is multiplied by (output index k); inverse: w^-1 and 1/N.
 void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int ncols, int logn, bool inverse,
-               const u64* prescale, const u64* postscale) {
+               u64 pre_base, const u64* postscale) {
   if (ncols <= 0) return;
   SBN_REQUIRE(logn >= 1 && logn <= 24, "ntt: unsupported size");
+  if (pre_base == 1) pre_base = 0;
   const NttTables& tb = get_ntt_tables(ctx, logn);
   const u64* W = inverse ? tb.w_inv : tb.w_fwd;
   const size_t N = size_t(1) << logn;
-  u64 scale = inverse ? gl_inv((u64)N) : 1;
   if (logn <= 11) {
+    const u64 scale = inverse ? gl_inv((u64)N) : 1;
+    const u64* prescale = pre_base ? get_pow_table(ctx, pre_base, logn) : nullptr;
     size_t smem = 2 * N * 8;
     int threads = N >= 4096 ? 256 : (N >= 512 ? (int)(N / 16) : 32);
     KScope ks(ctx, "ntt_small");
@@ -224,20 +310,12 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
     LAUNCH_CHECK(ctx);
     return;
   }
-  int l1 = logn / 2, l2 = logn - l1;
-  int logT1 = pick_logT(l1), logT2 = pick_logT(l2);
-  if (logT1 > l2) logT1 = l2;
-  if (logT2 > l1) logT2 = l1;
+  const int l1 = logn / 2, l2 = logn - l1;
+  const int logT1 = ntt_logT_of(l1), logT2 = ntt_logT_of(l2);
+  const u64* F = get_fourstep_table(ctx, logn, inverse, pre_base);
+  const u64* P1 = pre_base ? get_pow_table(ctx, gl_exp_pow2(pre_base, l2), l1) : nullptr;   // (c^N2)^n1
   auto tile_bytes = [](int l, int logT) { return ((size_t(1) << l) * ((size_t(1) << logT) + (logT > 0 ? 1 : 0)) + (size_t(1) << l)) * 8; };
   size_t smem1 = tile_bytes(l1, logT1), smem2 = tile_bytes(l2, logT2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
-  }
   // Column chunks sized so the intermediate stays L2-resident between the two passes.
   size_t chunk = (size_t(48) << 20) / (N * 8);
   if (chunk < 1) chunk = 1;
@@ -254,10 +332,10 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
     unsigned nc = (unsigned)std::min(chunk, (size_t)ncols - c0);
     dim3 g1((unsigned)(1u << (l2 - logT1)), nc), g2((unsigned)(1u << (l1 - logT2)), nc);
     { KScope ks(ctx, "ntt_pass1");
-    k_ntt_pass1<<<g1, 256, smem1, ctx->stream>>>(in + c0 * in_stride, in_stride, tmp, W, prescale, l1, l2, logT1);
+    NTT_DISPATCH_L(l1, (launch_pass1<L>(ctx, g1, smem1, pre_base != 0, in + c0 * in_stride, in_stride, tmp, W, F, P1, l2)));
     LAUNCH_CHECK(ctx); }
     KScope ks2(ctx, "ntt_pass2");
-    k_ntt_pass2<<<g2, 256, smem2, ctx->stream>>>(tmp, out + c0 * out_stride, out_stride, W, postscale, scale, l1, l2, logT2);
+    NTT_DISPATCH_L(l2, (launch_pass2<L>(ctx, g2, smem2, tmp, out + c0 * out_stride, out_stride, W, postscale, l1)));
     LAUNCH_CHECK(ctx);
   }
 }
@@ -265,7 +343,7 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
 // values (N) -> coefficients (N) for every column:  PolynomialValues::ifft
 void intt_columns(sbn_ctx* ctx, const u64* values, u64* coeffs, int ncols, int logn) {
   size_t N = size_t(1) << logn;
-  ntt_batch(ctx, values, N, coeffs, N, ncols, logn, true, nullptr, nullptr);
+  ntt_batch(ctx, values, N, coeffs, N, ncols, logn, true, 0, nullptr);
 }
 
 // coefficients (N) -> LDE values on the coset shift*<w_{N*2^r}>, laid out lde[col][b][k] with natural
@@ -277,7 +355,6 @@ void lde_columns(sbn_ctx* ctx, const u64* coeffs, u64* lde, int ncols, int logn,
   u64 wL = gl_root_of_unity(logn + rate_bits);
   for (int b = 0; b < R; b++) {
     u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, b));
-    const u64* pre = get_pow_table(ctx, sb, logn);
-    ntt_batch(ctx, coeffs, N, lde + (size_t)b * N, N * R, ncols, logn, false, pre, nullptr);
+    ntt_batch(ctx, coeffs, N, lde + (size_t)b * N, N * R, ncols, logn, false, sb, nullptr);
   }
 }

@@ -3,6 +3,6 @@
 const u64* get_pow_table(sbn_ctx* ctx, u64 base, int logn);
 const NttTables& get_ntt_tables(sbn_ctx* ctx, int logn);
 void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int ncols, int logn, bool inverse,
-               const u64* prescale, const u64* postscale);
+               u64 pre_base, const u64* postscale);
 void intt_columns(sbn_ctx* ctx, const u64* values, u64* coeffs, int ncols, int logn);
 void lde_columns(sbn_ctx* ctx, const u64* coeffs, u64* lde, int ncols, int logn, int rate_bits);

@@ -209,7 +209,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   fri_final_poly(ctx, views, logn, rate_bits, fri_alpha, zeta, zeta_next, fcoeffs);
   tm.mark("reduce batch of polynomials");
   u64 shift = GL_MULT_GENERATOR;
-  ntt_batch(ctx, fcoeffs, L, fvalues, L, 2, logL, false, get_pow_table(ctx, shift, logL), nullptr);
+  ntt_batch(ctx, fcoeffs, L, fvalues, L, 2, logL, false, shift, nullptr);
   tm.mark("perform final FFT");
   std::vector<FriLayer> layers(arities.size());
   std::vector<gl2> betas;
@@ -227,7 +227,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     fri_fold_coeffs(ctx, cur_coeffs, n, ab, beta, folded);
     shift = gl_pow(shift, (u64)1 << ab);
     cur_log -= ab;
-    ntt_batch(ctx, folded, m, vals, m, 2, cur_log, false, get_pow_table(ctx, shift, cur_log), nullptr);
+    ntt_batch(ctx, folded, m, vals, m, 2, cur_log, false, shift, nullptr);
     cur_coeffs = std::move(folded); cur_values = std::move(vals);
   }
   // final polynomial: truncate by the rate, observe

@@ -179,7 +179,7 @@ static void build_pi_binding(sbn_ctx* ctx, QArgs& a, const Segment& core, const 
   intt_columns(ctx, vals, coeffs, ncols, logn);
   lde = DevBuf<u64>(ctx, (size_t)ncols * 2 * N);
   for (int bq = 0; bq < 2; bq++)
-    ntt_batch(ctx, coeffs, N, lde + (size_t)bq * N, 2 * N, ncols, logn, false, get_pow_table(ctx, a.coset_shift[bq], logn), nullptr);
+    ntt_batch(ctx, coeffs, N, lde + (size_t)bq * N, 2 * N, ncols, logn, false, a.coset_shift[bq], nullptr);
   a.pi_lde = lde; a.pi_per_chal = per;
 }
 
@@ -266,7 +266,7 @@ void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_
   for (int c = 0; c < num_challenges; c++) {
     for (int bq = 0; bq < 2; bq++) {
       const u64* post = get_pow_table(ctx, gl_inv(a.coset_shift[bq]), logn);
-      ntt_batch(ctx, acc + ((size_t)c * 2 + bq) * N, N, u + (size_t)bq * N, N, 1, logn, true, nullptr, post);
+      ntt_batch(ctx, acc + ((size_t)c * 2 + bq) * N, N, u + (size_t)bq * N, N, 1, logn, true, 0, post);
     }
     k_quotient_split<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(u, u + N, out_chunks + (size_t)(2 * c) * N, out_chunks + (size_t)(2 * c + 1) * N, inv2, inv2gn, N);
     LAUNCH_CHECK(ctx);

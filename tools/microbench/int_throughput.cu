@@ -31,6 +31,14 @@ template <int MODE> __global__ void __launch_bounds__(256) k(u32* out, u32 seed)
       if (MODE == 12) asm volatile("{.reg .u32 t; mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c), "r"(seed));  // mad.lo.cc + madc.hi
       if (MODE == 13) { u64 t = w[i] * (u64)c; w[i] = t + (w[i] >> 3); }   // 64-bit mul.lo (compiler's choice)
       if (MODE == 14) w[i] = __umul64hi(w[i], w[i] | 1) + w[i];            // 64x64 high + add
+      if (MODE == 16) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c));                    // IDP.4A
+      if (MODE == 17) { asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c)); asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(b[i]) : "r"(a[i]), "r"(c)); }   // dp4a : IMAD 1:1
+      if (MODE == 18) { asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[i]), "r"(c)); }   // dp4a : LOP3 1:1
+      if (MODE == 19) { if (i % 4 == 0) asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};" : "+r"(a[i]), "+r"(a[i + 1]), "+r"(a[i + 2]), "+r"(a[i + 3]) : "r"(b[i]), "r"(b[i + 1]), "r"(c)); }   // 2 IMMA.16816 per body
+      if (MODE == 20) { if (i % 4 == 0) asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" : "+r"(a[i]), "+r"(a[i + 1]), "+r"(a[i + 2]), "+r"(a[i + 3]) : "r"(b[i]), "r"(b[i + 1]), "r"(b[i + 2]), "r"(b[i + 3]), "r"(c), "r"(seed)); }   // 2 IMMA.16832 per body
+      if (MODE == 21) { if (i % 4 == 0) asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};" : "+r"(a[i]), "+r"(a[i + 1]), "+r"(a[i + 2]), "+r"(a[i + 3]) : "r"(b[i]), "r"(b[i + 1]), "r"(c)); else asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(b[i]) : "r"(b[i]), "r"(c)); }   // 2 IMMA.16816 + 6 IMAD per body
+      if (MODE == 22) { asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[i]), "r"(c)); }   // IMAD : LOP3 1:1
+      if (MODE == 23) { asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(b[i]), "r"(c)); { u32 wl = (u32)w[i]; asm volatile("add.u32 %0, %0, %1;" : "+r"(wl) : "r"(c)); w[i] = wl; } }
       if (MODE == 15) asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w[i]) : "r"(a[i]), "r"(c), "l"(w[(i + 1) % CH]));   // IMAD.WIDE with a different addend register
     }
   }
@@ -41,8 +49,9 @@ template <int MODE> __global__ void __launch_bounds__(256) k(u32* out, u32 seed)
 }
 static const char* NAMES[] = {"IMAD.WIDE.U32 acc (mad.wide)", "IMAD.WIDE.U32 (mul.wide)", "IMAD 32 (mad.lo)", "IMAD.HI.U32 (mul.hi)", "IADD3 (add)", "IADD3+IADD3.X (64-bit add)",
                               "LOP3", "SHF", "PRMT", "mul.wide + add (1:1)", "mul.wide + 64-bit add (1:2)", "mad.lo + add (1:1)", "mad.lo.cc + madc.hi", "64-bit mul.lo + add", "umul64hi + add",
-                              "IMAD.WIDE acc, other addend"};
-static const int PTX_PER_ITER[] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 2, 3, 2, 2, 0, 0, 1};
+                              "IMAD.WIDE acc, other addend", "IDP.4A (dp4a)", "dp4a + mad.lo (1:1)", "dp4a + lop3 (1:1)", "2 IMMA m16n8k16 u8 per body", "2 IMMA m16n8k32 u8 per body",
+                              "2 IMMA.16816 + 6 IMAD per body", "mad.lo + lop3 (1:1)", "mad.lo + lop3 + add (1:1:1)"};
+static const int PTX_PER_ITER[] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 2, 3, 2, 2, 0, 0, 1, 1, 2, 2, 0, 0, 0, 2, 3};
 template <int MODE> void run(u32* d, int sms, double mhz) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   int blocks = sms * 8;
@@ -65,5 +74,6 @@ int main() {
   u32* d; cudaMalloc(&d, sms * 8 * 256 * 4);
   run<0>(d, sms, mhz); run<1>(d, sms, mhz); run<2>(d, sms, mhz); run<3>(d, sms, mhz); run<4>(d, sms, mhz); run<5>(d, sms, mhz); run<6>(d, sms, mhz); run<7>(d, sms, mhz);
   run<8>(d, sms, mhz); run<9>(d, sms, mhz); run<10>(d, sms, mhz); run<11>(d, sms, mhz); run<12>(d, sms, mhz); run<13>(d, sms, mhz); run<14>(d, sms, mhz); run<15>(d, sms, mhz);
+  run<16>(d, sms, mhz); run<17>(d, sms, mhz); run<18>(d, sms, mhz); run<19>(d, sms, mhz); run<20>(d, sms, mhz); run<21>(d, sms, mhz); run<22>(d, sms, mhz); run<23>(d, sms, mhz);
   return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
 }
