@@ -34,6 +34,11 @@ static __constant__ __align__(16) u32 d_poseidon_rc_dig[372 * 8] = {
     SBN_POSEIDON_RC_DIG_LIST};
 #endif
 #ifdef __CUDACC__
+static __constant__ __align__(16) u32 d_poseidon_rc_dig16[372 * 4] = {
+#include "poseidon_rc_dig16.inc"
+    SBN_POSEIDON_RC_DIG16_LIST};
+#endif
+#ifdef __CUDACC__
 // O(t)-per-round form of the 22 partial rounds (tools/gen_poseidon_fast.py; the table the host challenger uses):
 // per round g0, v[11], u[11]; then D^[11][11]; then e[12].
 static __constant__ u64 d_poseidon_fast[639] = {
@@ -165,6 +170,52 @@ __device__ __forceinline__ void poseidon_mds_dp4a(u64 s[12], int rc_off) {
         "}"
         : "=&r"(r0), "=&r"(r1)
         : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]));
+    s[r] = ((u64)r1 << 32) | r0;
+  }
+}
+// The same layer on 16-bit digits with the 2-way dot product (IDP.2A: two 16-bit values times two bytes): 4 digit sums per
+// output lane instead of 8 (each < 65535 * 292 + 65535 < 2^25), so half the packing and half the stitching; the number of
+// dot-product instructions is the same (12 lanes x 4 digits x 6 lane pairs).
+__device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b, u32 c) { u32 r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 dp2a_hi(u32 a, u32 b, u32 c) { u32 r; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], int rc_off) {
+  u32 A[4][6];   // A[d][j] = 16-bit digit d of lanes 2j (low half) and 2j+1 (high half)
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const u32 al = (u32)s[2 * j], ah = (u32)(s[2 * j] >> 32), bl = (u32)s[2 * j + 1], bh = (u32)(s[2 * j + 1] >> 32);
+    A[0][j] = prmt(al, bl, 0x5410); A[1][j] = prmt(al, bl, 0x7632);
+    A[2][j] = prmt(ah, bh, 0x5410); A[3][j] = prmt(ah, bh, 0x7632);
+  }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    const uint4 k = reinterpret_cast<const uint4*>(d_poseidon_rc_dig16)[rc_off + r];
+    u32 c[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const u32 m = SBN_MDS_WORD((4 * q + 12 - r) % 12) + ((r == 0 && q == 0) ? 8u : 0u);   // coefficients of lanes 4q .. 4q+3
+#pragma unroll
+      for (int d = 0; d < 4; d++) { c[d] = dp2a_lo(A[d][2 * q], m, c[d]); c[d] = dp2a_hi(A[d][2 * q + 1], m, c[d]); }
+    }
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 t1, t2, t3, t4, h, b, d, e, f;\n\t"
+        "shl.b32 t1, %3, 16;\n\t" "shr.u32 t2, %3, 16;\n\t" "add.u32 t3, t2, %4;\n\t"
+        "shl.b32 t4, %5, 16;\n\t" "shr.u32 h, %5, 16;\n\t"
+        "add.cc.u32 %0, %2, t1;\n\t"
+        "addc.cc.u32 %1, t3, t4;\n\t"
+        "addc.u32 h, h, 0;\n\t"              // value = h 2^64 + (%1:%0), h < 2^10
+        "sub.cc.u32 %0, %0, h;\n\t"          // + h (2^32 - 1)
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 b, 0, 0;\n\t"
+        "add.cc.u32 %1, %1, h;\n\t"
+        "addc.u32 d, b, 0;\n\t"              // net 64-bit wraps, in {-1, 0, 1}
+        "neg.s32 e, d;\n\t"
+        "shr.s32 f, d, 31;\n\t"
+        "add.cc.u32 %0, %0, e;\n\t"
+        "addc.u32 %1, %1, f;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
     s[r] = ((u64)r1 << 32) | r0;
   }
 }
@@ -304,7 +355,7 @@ HD void poseidon_permute(u64 s[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_nc(s[i], d_poseidon_rc[i]);
 #ifndef POSEIDON_MDS
-#define POSEIDON_MDS poseidon_mds_dp4a
+#define POSEIDON_MDS poseidon_mds_dp2a
 #endif
 #ifndef POSEIDON_LOOP_MODE
 #define POSEIDON_LOOP_MODE 0
