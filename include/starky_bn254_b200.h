@@ -100,6 +100,17 @@ int sbn_public_inputs(int air, const void* ios, size_t num_io, uint64_t* out, si
 /* K2-K6: `starky::prover::prove` */
 int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,
               sbn_proof** out);
+/* The same proof (byte-identical) computed by `world` = 2, 4, 8 or 16 cooperating contexts, one per GPU: intra-proof sharding of
+ * the LDE, the Merkle cap subtrees, the quotient evaluation and the query openings.  Every rank calls
+ * this with the same config, the same (replicated) trace and public inputs and its own rank; every rank returns the full proof.
+ * `allgather(user, send, nbytes, recv)` must deliver the `nbytes` of every rank, in rank order, into recv[world * nbytes] on
+ * every rank (host memory; NCCL / gloo all_gather in the Python mirror) and return 0.  It is called the same number of times
+ * with the same sizes on every rank: once per commitment (cap digests), once for the quotient values, once for the opened rows.
+ * Needs rate_bits = 1 and world <= 2^cap_height.  world = 1 is sbn_prove. */
+typedef int (*sbn_allgather_fn)(void* user, const void* send, size_t nbytes, void* recv);
+typedef struct { uint32_t rank, world; sbn_allgather_fn allgather; void* user; } sbn_shard;
+int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,
+                      const sbn_shard* shard, sbn_proof** out);
 /* Canonical little-endian wire format (DESIGN.md "Proof wire format").  Call with buf == NULL to get the length. */
 int sbn_proof_serialize(const sbn_proof* proof, uint8_t* buf, size_t* len);
 /* JSON object of per-phase device milliseconds of the sbn_prove call that produced `proof` */

@@ -45,6 +45,14 @@ class StarkConfig(C.Structure):
 _lib = None
 
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class Shard(C.Structure):
+    """sbn_shard (include/starky_bn254_b200.h): this rank's place in an intra-proof sharding group."""
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", C.c_void_p)]
+
+
 def lib():
     """Loads the CUDA library; fails loudly if it has not been built (no fallback path exists)."""
     global _lib
@@ -75,6 +83,7 @@ def lib():
         L.sbn_trace_free.argtypes = [vp]
         L.sbn_public_inputs.argtypes = [C.c_int, vp, sz, u64p, sz]
         L.sbn_prove.argtypes = [vp, vp, vp, u64p, sz, C.POINTER(vp)]
+        L.sbn_prove_sharded.argtypes = [vp, vp, vp, u64p, sz, C.POINTER(Shard), C.POINTER(vp)]
         L.sbn_proof_serialize.argtypes = [vp, vp, C.POINTER(sz)]
         L.sbn_proof_timings.argtypes = [vp, C.c_char_p, sz]
         L.sbn_proof_debug.argtypes = [vp, C.c_int, u64p, sz, C.POINTER(sz)]
@@ -313,6 +322,37 @@ def prove(stark, config, trace, public_inputs, timing=None):
     pi = np.ascontiguousarray(public_inputs, dtype=np.uint64)
     h = C.c_void_p()
     ctx.check(lib().sbn_prove(ctx.h, C.byref(config), trace.h, _ptr(pi), len(pi), C.byref(h)))
+    proof = StarkProofWithPublicInputs(ctx, h)
+    if timing is not None:
+        timing.update(proof.timings)
+    return proof
+
+
+def prove_sharded(stark, config, trace, public_inputs, rank, world, allgather, timing=None):
+    """One proof computed by `world` (2, 4, 8, 16) cooperating ranks, one GPU each: `sbn_prove_sharded`.  Every rank passes the
+    same (replicated) trace and public inputs and gets the full proof, byte-identical to `prove`'s.  `allgather(data: bytes)`
+    returns the list of every rank's `data` in rank order (see sharding.dist_allgather / sharding.ThreadGroup)."""
+    ctx = trace.ctx
+    pi = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+    failure = []
+
+    def cb(user, send, nbytes, recv):
+        try:
+            parts = allgather(C.string_at(send, nbytes))
+            if len(parts) != world or any(len(x) != nbytes for x in parts):
+                raise ValueError("all-gather returned %s parts of sizes %s, expected %d x %d" % (len(parts), [len(x) for x in parts][:4], world, nbytes))
+            C.memmove(recv, b"".join(parts), nbytes * world)
+            return 0
+        except BaseException as e:  # never let an exception cross the C frames
+            failure.append(e)
+            return 1
+
+    shard = Shard(rank, world, ALLGATHER_FN(cb), None)
+    h = C.c_void_p()
+    rc = lib().sbn_prove_sharded(ctx.h, C.byref(config), trace.h, _ptr(pi), len(pi), C.byref(shard), C.byref(h))
+    if failure:
+        raise failure[0]
+    ctx.check(rc)
     proof = StarkProofWithPublicInputs(ctx, h)
     if timing is not None:
         timing.update(proof.timings)

@@ -358,3 +358,40 @@ void lde_columns(sbn_ctx* ctx, const u64* coeffs, u64* lde, int ncols, int logn,
     ntt_batch(ctx, coeffs, N, lde + (size_t)b * N, N * R, ncols, logn, false, sb, nullptr);
   }
 }
+
+// ---- one LDE class (intra-proof sharding) ----
+// The leaves under Merkle cap entries [r 2^(cap_height - m), (r + 1) 2^(cap_height - m)) are the LDE points of natural index
+// i = rho (mod G), G = 2^m, rho = bitrev_m(r): the coset s w_L^rho <w_(L/G)>.  lde_class evaluates every column on that
+// coset only: out[col][b'][k'] with i = rho + G (k' B' + b'), B' = max(1, R / G) -- the layout lde_columns would give for a
+// domain of L / G points, so the leaf-hash, quotient and query kernels run on it unchanged.
+//   G <= R: the class is R / G whole sub-cosets b = rho + G b' of the size-N transform;
+//   G >  R: L / G < N points: reduce the polynomial mod x^(L/G) - a, a = (s w_L^rho)^(L/G), then one size-L/G coset transform.
+__global__ void k_fold_mod_binomial(const u64* __restrict__ coeffs, size_t N, u64* __restrict__ out, size_t Lp, int f, u64 a) {
+  const size_t n = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (n >= Lp) return;
+  const u64* c = coeffs + (size_t)blockIdx.y * N + n;
+  u64 acc = 0, ap = 1;
+  for (int j = 0; j < f; j++) { acc = gl_add(acc, gl_mul(c[(size_t)j * Lp], ap)); ap = gl_mul(ap, a); }
+  out[(size_t)blockIdx.y * Lp + n] = acc;
+}
+void lde_class(sbn_ctx* ctx, const u64* coeffs, u64* out, int ncols, int logn, int rate_bits, int m, u32 rho) {
+  const size_t N = size_t(1) << logn;
+  const int R = 1 << rate_bits, G = 1 << m;
+  const u64 wL = gl_root_of_unity(logn + rate_bits);
+  if (G <= R) {
+    const int Bp = R / G;
+    for (int bp = 0; bp < Bp; bp++) {
+      const u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, rho + (u64)G * bp));
+      ntt_batch(ctx, coeffs, N, out + (size_t)bp * N, N * Bp, ncols, logn, false, sb, nullptr);
+    }
+    return;
+  }
+  const int logLp = logn + rate_bits - m, f = G / R;
+  const size_t Lp = size_t(1) << logLp;
+  const u64 c = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, rho));
+  DevBuf<u64> folded(ctx, (size_t)ncols * Lp);
+  { KScope ks(ctx, "lde_fold");
+    k_fold_mod_binomial<<<dim3((unsigned)((Lp + 255) / 256), (unsigned)ncols), 256, 0, ctx->stream>>>(coeffs, N, folded, Lp, f, gl_exp_pow2(c, logLp));
+    LAUNCH_CHECK(ctx); }
+  ntt_batch(ctx, folded, Lp, out, Lp, ncols, logLp, false, c, nullptr);
+}

@@ -58,22 +58,56 @@ struct sbn_proof {
   std::vector<u64> dbg_z, dbg_q, dbg_ch;
 };
 
-// Commitment to a batch of polynomials (plonky2 `PolynomialBatch`, blinding = false).
-struct Commitment {
-  DevBuf<u64> coeffs, lde; DevMerkleTree tree; int ncols = 0;
+// Intra-proof sharding over world = 2^m ranks: rank r commits to, evaluates the quotient on and
+// answers queries for the LDE class rho = bitrev_m(r) (natural LDE indices i = rho mod 2^m), which is exactly the set of leaves
+// under Merkle cap entries [r 2^(cap_height - m), (r + 1) 2^(cap_height - m)).  Everything else (trace, coefficients, Z, openings,
+// FRI layers, transcript) is replicated and deterministic, so the only exchanges are all-gathers of cap digests, of the
+// quotient values (2 N num_challenges field elements in total) and of the opened rows with their paths.
+struct Shard {
+  int rank = 0, world = 1, m = 0; sbn_allgather_fn allgather = nullptr; void* user = nullptr;
+  bool on() const { return world > 1; }
+  u32 rho() const { return bitrev32((u32)rank, m); }
+  void gather(const void* send, size_t nbytes, std::vector<uint8_t>& recv) const {
+    recv.resize(nbytes * world);
+    int rc = allgather(user, send, nbytes, recv.data());
+    if (rc != 0) throw SbnError(SBN_ERR_INTERNAL, "sharded prove: the all-gather callback failed");
+  }
 };
-static void commit_from_coeffs(sbn_ctx* ctx, Commitment& c, int ncols, int logn, int rate_bits, int cap_height) {
+
+// Commitment to a batch of polynomials (plonky2 `PolynomialBatch`, blinding = false).  Sharded: `lde` / `tree` hold this rank's
+// class only ([col][2N / world], local leaf order), `lde_next` the class the quotient's "next" rows come from when world > 2.
+struct Commitment {
+  DevBuf<u64> coeffs, lde, lde_next; DevMerkleTree tree; int ncols = 0;
+  std::vector<u64> cap;   // the full cap (2^cap_height x 4), identical on every rank
+};
+static void commit_from_coeffs(sbn_ctx* ctx, const Shard& sh, Commitment& c, int ncols, int logn, int rate_bits, int cap_height, bool need_next) {
   size_t N = size_t(1) << logn;
   c.ncols = ncols;
-  c.lde = DevBuf<u64>(ctx, (size_t)ncols * (N << rate_bits));
-  lde_columns(ctx, c.coeffs, c.lde, ncols, logn, rate_bits);
-  merkle_commit_lde(ctx, c.lde, ncols, logn, rate_bits, cap_height, &c.tree);
+  if (!sh.on()) {
+    c.lde = DevBuf<u64>(ctx, (size_t)ncols * (N << rate_bits));
+    lde_columns(ctx, c.coeffs, c.lde, ncols, logn, rate_bits);
+    merkle_commit_lde(ctx, c.lde, ncols, logn, rate_bits, cap_height, &c.tree);
+    c.cap = c.tree.cap;
+    return;
+  }
+  const size_t Lp = (N << rate_bits) >> sh.m;
+  c.lde = DevBuf<u64>(ctx, (size_t)ncols * Lp);
+  lde_class(ctx, c.coeffs, c.lde, ncols, logn, rate_bits, sh.m, sh.rho());
+  if (need_next && sh.world > 2) {
+    c.lde_next = DevBuf<u64>(ctx, (size_t)ncols * Lp);
+    lde_class(ctx, c.coeffs, c.lde_next, ncols, logn, rate_bits, sh.m, (sh.rho() + 2) & (sh.world - 1));
+  }
+  merkle_commit_lde(ctx, c.lde, ncols, logn + rate_bits - sh.m, 0, cap_height - sh.m, &c.tree);
+  std::vector<uint8_t> all;
+  sh.gather(c.tree.cap.data(), c.tree.cap.size() * 8, all);
+  c.cap.resize(all.size() / 8);
+  memcpy(c.cap.data(), all.data(), all.size());
 }
-static void commit_from_values(sbn_ctx* ctx, Commitment& c, const u64* values, int ncols, int logn, int rate_bits, int cap_height) {
+static void commit_from_values(sbn_ctx* ctx, const Shard& sh, Commitment& c, const u64* values, int ncols, int logn, int rate_bits, int cap_height, bool need_next) {
   size_t N = size_t(1) << logn;
   c.coeffs = DevBuf<u64>(ctx, (size_t)ncols * N);
   intt_columns(ctx, values, c.coeffs, ncols, logn);
-  commit_from_coeffs(ctx, c, ncols, logn, rate_bits, cap_height);
+  commit_from_coeffs(ctx, sh, c, ncols, logn, rate_bits, cap_height, need_next);
 }
 
 struct Writer {  // canonical proof wire format: LE u64 field elements, u32 length prefixes, u8 option tag
@@ -96,7 +130,7 @@ static std::vector<int> reduction_arity_bits(const sbn_config& c, int degree_bit
   return r;
 }
 
-static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr, const u64* public_inputs, size_t npis, sbn_proof* proof) {
+static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr, const u64* public_inputs, size_t npis, const Shard& sh, sbn_proof* proof) {
   const AirDesc& air = tr->air;
   const int logn = tr->logn, rate_bits = cfg.rate_bits, cap_height = cfg.cap_height, nch = cfg.num_challenges;
   const size_t N = size_t(1) << logn, L = N << rate_bits;
@@ -108,17 +142,21 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   std::vector<int> arities = reduction_arity_bits(cfg, logn);
   int total_arities = 0; for (int a : arities) total_arities += a;
   SBN_REQUIRE(total_arities <= logn + rate_bits - cap_height, "FRI total reduction arity is too large.");
+  if (sh.on()) {
+    SBN_REQUIRE(sh.allgather && (1 << sh.m) == sh.world && sh.rank >= 0 && sh.rank < sh.world, "sharded prove: world must be a power of two and the all-gather callback set");
+    SBN_REQUIRE(rate_bits == 1 && sh.m <= cap_height && sh.m < logn, "sharded prove: needs rate_bits = 1 and world <= 2^cap_height");
+  }
   for (size_t i = 0; i < npis; i++) SBN_REQUIRE(public_inputs[i] < GL_P, "public input is not a canonical field element");
   PhaseTimer tm(ctx);
   Writer w(proof->bytes);
 
   // ---- trace commitment ----
   Commitment trace_c;
-  commit_from_values(ctx, trace_c, tr->cols, (int)air.num_columns, logn, rate_bits, cap_height);
+  commit_from_values(ctx, sh, trace_c, tr->cols, (int)air.num_columns, logn, rate_bits, cap_height, true);
   tm.mark("compute trace commitment");
   Challenger ch;
-  ch.observe_n(trace_c.tree.cap.data(), trace_c.tree.cap.size());
-  w.hashes(trace_c.tree.cap.data(), trace_c.tree.cap.size() / 4);
+  ch.observe_n(trace_c.cap.data(), trace_c.cap.size());
+  w.hashes(trace_c.cap.data(), trace_c.cap.size() / 4);
 
   // ---- permutation argument ----
   const int qdf = air.quotient_degree_factor();
@@ -149,10 +187,10 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
       CUDA_CHECK(cudaMemcpyAsync(proof->dbg_z.data(), zvals, nz * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
-    commit_from_values(ctx, z_c, zvals, (int)nz, logn, rate_bits, cap_height);
+    commit_from_values(ctx, sh, z_c, zvals, (int)nz, logn, rate_bits, cap_height, true);
     tm.mark("compute permutation Z commitments");
-    ch.observe_n(z_c.tree.cap.data(), z_c.tree.cap.size());
-    w.u8(1); w.hashes(z_c.tree.cap.data(), z_c.tree.cap.size() / 4);
+    ch.observe_n(z_c.cap.data(), z_c.cap.size());
+    w.u8(1); w.hashes(z_c.cap.data(), z_c.cap.size() / 4);
   } else {
     w.u8(0);
   }
@@ -165,17 +203,44 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   Commitment q_c;
   const int nq_polys = qdf * nch;
   q_c.coeffs = DevBuf<u64>(ctx, (size_t)nq_polys * N);
-  compute_quotient_chunks(ctx, air, trace_c.lde, uses_perm ? z_c.lde.get() : nullptr, perm, d_pis, alphas, nch, logn, rate_bits, q_c.coeffs);
+  if (!sh.on()) {
+    compute_quotient_chunks(ctx, air, trace_c.lde, uses_perm ? z_c.lde.get() : nullptr, perm, d_pis, alphas, nch, logn, rate_bits, q_c.coeffs);
+  } else {
+    // this rank's class of the quotient coset (rate_bits = 1: the quotient coset is the LDE coset), then all classes -> [chal][bq][k]
+    QDomain dom; dom.m = sh.m; dom.sigma = sh.rho();
+    dom.trace = trace_c.lde; dom.trace_next = sh.world > 2 ? trace_c.lde_next.get() : trace_c.lde.get();
+    if (uses_perm) { dom.zs = z_c.lde; dom.zs_next = sh.world > 2 ? z_c.lde_next.get() : z_c.lde.get(); }
+    const size_t Mp = quotient_points(dom, logn);
+    DevBuf<u64> acc_local(ctx, (size_t)SBN_MAX_CHALLENGES * Mp), acc_full(ctx, (size_t)nch * 2 * N);
+    quotient_eval(ctx, air, dom, nullptr, nullptr, perm, d_pis, alphas, nch, logn, rate_bits, acc_local);
+    std::vector<u64> mine((size_t)nch * Mp), full((size_t)nch * 2 * N);
+    CUDA_CHECK(cudaMemcpyAsync(mine.data(), acc_local, mine.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint8_t> all;
+    sh.gather(mine.data(), mine.size() * 8, all);
+    const u64* parts = reinterpret_cast<const u64*>(all.data());
+    for (int r = 0; r < sh.world; r++) {
+      const size_t sigma = bitrev32((u32)r, sh.m);
+      for (int c = 0; c < nch; c++) {
+        const u64* src = parts + ((size_t)r * nch + c) * Mp;
+        u64* dst = full.data() + (size_t)c * 2 * N;
+        for (size_t t = 0; t < Mp; t++) { const size_t iq = sigma + ((size_t)t << sh.m); dst[(iq & 1) * N + (iq >> 1)] = src[t]; }
+      }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(acc_full, full.data(), full.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    quotient_finish(ctx, acc_full, nch, logn, q_c.coeffs);
+  }
   tm.mark("compute quotient polys");
   if (getenv("SBN_DEBUG_INTERMEDIATES")) {
     proof->dbg_q.resize((size_t)nq_polys * N);
     CUDA_CHECK(cudaMemcpyAsync(proof->dbg_q.data(), q_c.coeffs, proof->dbg_q.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
-  commit_from_coeffs(ctx, q_c, nq_polys, logn, rate_bits, cap_height);
+  commit_from_coeffs(ctx, sh, q_c, nq_polys, logn, rate_bits, cap_height, false);
   tm.mark("compute quotient commitment");
-  ch.observe_n(q_c.tree.cap.data(), q_c.tree.cap.size());
-  w.hashes(q_c.tree.cap.data(), q_c.tree.cap.size() / 4);
+  ch.observe_n(q_c.cap.data(), q_c.cap.size());
+  w.hashes(q_c.cap.data(), q_c.cap.size() / 4);
 
   // ---- openings ----
   gl2 zeta = ch.get_ext();
@@ -252,14 +317,30 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   for (auto& x : indices) x = ch.get() % L;
   std::vector<QueryOracle> qo; qo.push_back({trace_c.lde, C, &trace_c.tree}); if (Z) qo.push_back({z_c.lde, Z, &z_c.tree}); qo.push_back({q_c.lde, nq_polys, &q_c.tree});
   std::vector<FriLayer*> lp; for (auto& l : layers) lp.push_back(&l);
-  size_t rw = fri_query_record_words(qo, lp);
-  std::vector<u64> rec(rw * indices.size());
-  fri_gather_queries(ctx, qo, logn, rate_bits, lp, indices, rec.data());
+  const size_t rw_o = fri_query_record_words(qo, {}), rw_l = fri_query_record_words({}, lp), nq = indices.size();
+  std::vector<u64> rec_o(rw_o * nq), rec_l(rw_l * nq);
+  if (!sh.on()) {
+    fri_gather_queries(ctx, qo, logn, rate_bits, {}, indices, rec_o.data());
+  } else {
+    // the rank that owns a leaf opens it: rows and paths live in its class batches, at the leaf's index inside the class
+    const int logLp = logL - sh.m;
+    std::vector<u64> local_idx; std::vector<size_t> which;
+    for (size_t q = 0; q < nq; q++) if ((int)(indices[q] >> logLp) == sh.rank) { local_idx.push_back(indices[q] & ((u64(1) << logLp) - 1)); which.push_back(q); }
+    std::vector<u64> mine(rw_o * nq, 0), got(rw_o * local_idx.size());
+    if (!local_idx.empty()) fri_gather_queries(ctx, qo, logLp, 0, {}, local_idx, got.data());
+    for (size_t j = 0; j < which.size(); j++) memcpy(mine.data() + which[j] * rw_o, got.data() + j * rw_o, rw_o * 8);
+    std::vector<uint8_t> all;
+    sh.gather(mine.data(), mine.size() * 8, all);
+    const u64* parts = reinterpret_cast<const u64*>(all.data());
+    for (size_t q = 0; q < nq; q++) memcpy(rec_o.data() + q * rw_o, parts + ((size_t)(indices[q] >> logLp) * nq + q) * rw_o, rw_o * 8);
+  }
+  fri_gather_queries(ctx, {}, logn, rate_bits, lp, indices, rec_l.data());
   w.u32_((uint32_t)indices.size());
   for (size_t q = 0; q < indices.size(); q++) {
-    const u64* r = rec.data() + q * rw;
+    const u64* r = rec_o.data() + q * rw_o;
     w.u32_((uint32_t)qo.size());
     for (auto& o : qo) { w.fvec(r, o.ncols); r += o.ncols; w.hashes(r, o.tree->proof_len()); r += (size_t)o.tree->proof_len() * 4; }
+    r = rec_l.data() + q * rw_l;
     w.u32_((uint32_t)lp.size());
     for (auto* l : lp) { size_t ne = size_t(1) << l->arity_bits; w.evec(r, ne); r += 2 * ne; w.hashes(r, l->tree.proof_len()); r += (size_t)l->tree.proof_len() * 4; }
   }
@@ -309,6 +390,7 @@ void sbn_ctx_destroy(sbn_ctx* ctx) {
   ctx->kresolve();
   for (auto e : ctx->kpool) cudaEventDestroy(e);
   for (auto& kv : ctx->pow_tables) cudaFree(kv.second);
+  for (auto& kv : ctx->fourstep_tables) cudaFree(kv.second);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -411,7 +493,21 @@ int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, co
   SBN_REQUIRE(trace->ctx == ctx, "trace belongs to another context");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   std::unique_ptr<sbn_proof> p(new sbn_proof());
-  prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, p.get());
+  prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, Shard(), p.get());
+  *out = p.release();
+  API_END(ctx)
+}
+int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,
+                      const sbn_shard* shard, sbn_proof** out) {
+  API_BEGIN
+  SBN_REQUIRE(ctx && config && trace && out && shard && (public_inputs || num_public_inputs == 0), "null argument");
+  SBN_REQUIRE(trace->ctx == ctx, "trace belongs to another context");
+  SBN_REQUIRE(shard->world >= 1 && shard->world <= 16 && (shard->world & (shard->world - 1)) == 0 && shard->rank < shard->world, "bad shard description");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  Shard sh; sh.rank = (int)shard->rank; sh.world = (int)shard->world; sh.allgather = shard->allgather; sh.user = shard->user;
+  while ((1 << sh.m) < sh.world) sh.m++;
+  std::unique_ptr<sbn_proof> p(new sbn_proof());
+  prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, sh, p.get());
   *out = p.release();
   API_END(ctx)
 }
@@ -477,7 +573,7 @@ int sbn_commit_columns(sbn_ctx* ctx, const uint64_t* values, size_t ncols, int l
   DevBuf<u64> d_vals(ctx, ncols * N);
   CUDA_CHECK(cudaMemcpyAsync(d_vals, values, ncols * N * 8, cudaMemcpyHostToDevice, ctx->stream));
   Commitment c;
-  commit_from_values(ctx, c, d_vals, (int)ncols, logn, rate_bits, cap_height);
+  commit_from_values(ctx, Shard(), c, d_vals, (int)ncols, logn, rate_bits, cap_height, false);
   if (coeffs_out) CUDA_CHECK(cudaMemcpyAsync(coeffs_out, c.coeffs, ncols * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (lde_out) {
     DevBuf<u64> nat(ctx, ncols * L);

@@ -8,24 +8,23 @@
 #include "ntt.cuh"
 
 HD void qpoint_begin(const QArgs& a, size_t idx, QPoint& q) {
-  const size_t N = size_t(1) << a.logn;
-  const int bq = (int)(idx >> a.logn);
-  const size_t k = idx & (N - 1), kn = (k + 1) & (N - 1);
-  q.lp = a.trace + a.coset_off[bq] + k;
-  q.np = a.trace + a.coset_off[bq] + kn;
+  const size_t M = size_t(1) << a.logm;
+  const int sg = (int)(idx >> a.logm);
+  const size_t k = idx & (M - 1), kn = (k + a.next_shift) & (M - 1);
+  q.lp = a.trace + a.seg_off[sg] + k;
+  q.np = a.trace_next + a.seg_off[sg] + kn;
   q.stride = a.trace_stride;
   q.pi = a.pi;
-  F x(gl_mul(a.coset_shift[bq], a.wpow[k]));
+  F x(gl_mul(a.seg_shift[sg], a.wpow[k]));
   q.z_last = x - F(a.w_inv);
-  q.l_first = F(a.lagrange[a.coset_off[bq] + k]);
-  q.l_last = F(a.lagrange[a.lagrange_stride + a.coset_off[bq] + k]);
+  q.l_first = F(a.lagrange[a.seg_off[sg] + k]);
+  q.l_last = F(a.lagrange[a.lagrange_stride + a.seg_off[sg] + k]);
   for (int c = 0; c < SBN_MAX_CHALLENGES; c++) { q.alpha[c] = F(a.alpha[c]); q.acc[c] = F(); q.pi_skip[c] = F(a.pi_skip[c]); }
-  q.pic = a.pi_lde + idx; q.pic_stride = N << 1; q.pic_per_chal = a.pi_per_chal;
+  q.pic = a.pi_lde + idx; q.pic_stride = a.npoints; q.pic_per_chal = a.pi_per_chal;
 }
 HD void qpoint_end(const QArgs& a, size_t idx, const QPoint& q) {
-  const size_t N2 = size_t(2) << a.logn;
   for (int c = 0; c < SBN_MAX_CHALLENGES; c++) {
-    u64* p = a.acc + (size_t)c * N2 + idx;
+    u64* p = a.acc + (size_t)c * a.npoints + idx;
     F prev = a.first ? F() : F(*p) * F(a.alpha_m[c]);
     *p = (prev + q.acc[c]).v;
   }
@@ -34,11 +33,11 @@ HD void qpoint_end(const QArgs& a, size_t idx, const QPoint& q) {
 // starky `eval_permutation_checks`: first-row Z-1 for every Z, then one product
 // constraint per Z.  2*nz constraints.
 HD void eval_permutation_checks(const QArgs& a, size_t idx, QPoint& q) {
-  const size_t N = size_t(1) << a.logn;
-  const int bq = (int)(idx >> a.logn);
-  const size_t k = idx & (N - 1), kn = (k + 1) & (N - 1);
-  const u64* zl = a.zs + a.coset_off[bq] + k;
-  const u64* zn = a.zs + a.coset_off[bq] + kn;
+  const size_t M = size_t(1) << a.logm;
+  const int sg = (int)(idx >> a.logm);
+  const size_t k = idx & (M - 1), kn = (k + a.next_shift) & (M - 1);
+  const u64* zl = a.zs + a.seg_off[sg] + k;
+  const u64* zn = a.zs_next + a.seg_off[sg] + kn;
   for (int i = 0; i < a.nz; i++) q.first_row(F(zl[(size_t)i * a.zs_stride]) - F(1));
   for (int i = 0; i < a.nz; i++) {
     F lhs(1), rhs(1);
@@ -72,7 +71,7 @@ HD void eval_segment(const QArgs& a, const Segment& s, size_t idx, QPoint& q) {
     case SEG_G2_ADD: eval_g2_add(q, q.lv(s.p1), s.p0); break;
     case SEG_G2_DOUBLE: eval_g2_double(q, q.lv(s.p1), s.p0); break;
     case SEG_FQ12_CORE: eval_fq12_exp_core(q, s.p0, s.p1, s.p2 != 0); break;
-    case SEG_FQ12_MUL: eval_fq12_mul(q, q.lv(s.p0), a.scratch + idx, size_t(2) << a.logn); break;
+    case SEG_FQ12_MUL: eval_fq12_mul(q, q.lv(s.p0), a.scratch + idx, a.npoints); break;
     case SEG_FLAGS_U64: eval_flags_u64(q, s.p0); break;
   }
 }
@@ -84,7 +83,7 @@ HD void eval_segment(const QArgs& a, const Segment& s, size_t idx, QPoint& q) {
 //   re[m] = sum_{i+j=m} (x_i y_j - x_{i+6} y_{j+6}),  im[m] = sum_{i+j=m} (x_i y_{j+6} + x_{i+6} y_j)
 __global__ void __launch_bounds__(128) k_fq12_products(QArgs a, int xa, int ya, u64* __restrict__ prod) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t N2 = size_t(2) << a.logn;
+  const size_t N2 = a.npoints;
   if (idx >= N2) return;
   const int oi = blockIdx.y;
   QPoint q;
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(128) k_fq12_products(QArgs a, int xa, int ya, 
 
 template <int KIND> __global__ void __launch_bounds__(128) k_segment(QArgs a, Segment s) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (idx >= (size_t(2) << a.logn)) return;
+  if (idx >= a.npoints) return;
   QPoint q;
   qpoint_begin(a, idx, q);
   Segment ss = s; ss.kind = (SegKind)KIND;   // compile-time kind: each instantiation keeps only its own code
@@ -116,7 +115,7 @@ static const char* seg_name(SegKind k) {
   return "q_other";
 }
 static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
-  unsigned blocks = (unsigned)(((size_t(2) << a.logn) + 127) / 128);
+  unsigned blocks = (unsigned)((a.npoints + 127) / 128);
   if (s.kind == SEG_FQ12_MUL) {   // x = a; y = a (square) or b (mul): columns 0 / 192 of the row
     KScope kp(ctx, "q_fq12_products");
     k_fq12_products<<<dim3(blocks, 12), 128, 0, ctx->stream>>>(a, 0, s.p1 ? 0 : 192, a.scratch);
@@ -155,8 +154,8 @@ __global__ void k_pi_columns(u64* __restrict__ vals, size_t N, const u64* __rest
     }
   }
 }
-// Returns the low-degree extension of the binding columns on the two quotient cosets: out[col][bq][k].
-static void build_pi_binding(sbn_ctx* ctx, QArgs& a, const Segment& core, const u64* d_public_inputs, int num_challenges, DevBuf<u64>& lde) {
+// Returns the low-degree extension of the binding columns on the evaluation points: out[col][point].
+static void build_pi_binding(sbn_ctx* ctx, QArgs& a, const QDomain& dom, const Segment& core, const u64* d_public_inputs, int num_challenges, DevBuf<u64>& lde) {
   const int group_count = core.kind == SEG_FQ_CORE ? 1 : core.kind == SEG_G1_CORE ? 2 : core.kind == SEG_G2_CORE ? 4 : (core.p2 ? -1 : 0);
   num_challenges = SBN_MAX_CHALLENGES;   // unused challenges have alpha = 0; their columns exist so the kernel never reads out of bounds
   const int num_io = core.p0, io_len = pi_io_len(group_count), per = io_len + 2, ncols = 1 + num_challenges * per;
@@ -177,9 +176,8 @@ static void build_pi_binding(sbn_ctx* ctx, QArgs& a, const Segment& core, const 
   LAUNCH_CHECK(ctx);
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `ha` is pageable host memory
   intt_columns(ctx, vals, coeffs, ncols, logn);
-  lde = DevBuf<u64>(ctx, (size_t)ncols * 2 * N);
-  for (int bq = 0; bq < 2; bq++)
-    ntt_batch(ctx, coeffs, N, lde + (size_t)bq * N, 2 * N, ncols, logn, false, a.coset_shift[bq], nullptr);
+  lde = DevBuf<u64>(ctx, (size_t)ncols * a.npoints);
+  lde_class(ctx, coeffs, lde, ncols, logn, 1, dom.m, dom.sigma);   // m = 0: both half-cosets, [col][bq][k]
   a.pi_lde = lde; a.pi_per_chal = per;
 }
 
@@ -189,12 +187,11 @@ __global__ void k_fill_lagrange_coeffs(u64* coeffs, const u64* wpow, u64 ninv, s
   coeffs[j] = ninv;                      // ifft(selector(0))      = 1/N
   coeffs[N + j] = gl_mul(ninv, wpow[j]);  // ifft(selector(N - 1))  = w^j / N
 }
-__global__ void k_scale_cosets(u64* acc, int logn, int num_challenges, u64 zh0, u64 zh1) {
+__global__ void k_scale_cosets(u64* acc, int logm, size_t npoints, int num_challenges, u64 zh0, u64 zh1) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t N2 = size_t(2) << logn;
-  if (i >= N2 * num_challenges) return;
-  int bq = (int)((i % N2) >> logn);
-  acc[i] = gl_mul(acc[i], bq ? zh1 : zh0);
+  if (i >= npoints * num_challenges) return;
+  int sg = (int)((i % npoints) >> logm);
+  acc[i] = gl_mul(acc[i], sg ? zh1 : zh0);
 }
 // f_lo = (u0 + u1)/2, f_hi = (u0 - u1)/(2 g^N): the two degree-N chunks of a degree-2N quotient
 // from its unscaled per-coset interpolants u_b = f_lo + (-1)^b g^N f_hi.
@@ -206,28 +203,41 @@ __global__ void k_quotient_split(const u64* u0, const u64* u1, u64* lo, u64* hi,
   hi[j] = gl_mul(gl_sub(a, b), inv2gn);
 }
 
-void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_lde, const u64* zs_lde, const PermInstances& perm,
-                             const u64* d_public_inputs, const u64* alphas, int num_challenges, int logn, int rate_bits, u64* out_chunks) {
+size_t quotient_points(const QDomain& dom, int logn) { return (size_t(2) << logn) >> dom.m; }
+
+void quotient_eval(sbn_ctx* ctx, const AirDesc& air, const QDomain& dom, const u64* trace_lde, const u64* zs_lde, const PermInstances& perm,
+                   const u64* d_public_inputs, const u64* alphas, int num_challenges, int logn, int rate_bits, u64* d_acc) {
   SBN_REQUIRE(air.quotient_degree_factor() == 2, "only constraint_degree 3 (quotient degree factor 2) is supported");
   SBN_REQUIRE(rate_bits >= 1, "constraint degree higher than the rate is not supported");
   SBN_REQUIRE(num_challenges >= 1 && num_challenges <= SBN_MAX_CHALLENGES, "unsupported num_challenges");
+  SBN_REQUIRE(dom.m == 0 || (rate_bits == 1 && dom.m <= logn), "sharded quotient evaluation needs rate_bits = 1");
   const size_t N = size_t(1) << logn, R = size_t(1) << rate_bits, L = N * R;
   const size_t step = size_t(1) << (rate_bits - 1);
+  const u64 w2n = gl_root_of_unity(logn + 1);
+  QArgs a; memset(&a, 0, sizeof a);
+  a.logn = logn;
+  if (dom.m == 0) {   // two half-cosets inside the LDE batches
+    a.logm = logn; a.nseg = 2; a.npoints = 2 * N; a.next_shift = 1;
+    a.trace = a.trace_next = trace_lde; a.trace_stride = L; a.zs = a.zs_next = zs_lde; a.zs_stride = L;
+    for (int bq = 0; bq < 2; bq++) { a.seg_off[bq] = (size_t)bq * step * N; a.seg_shift[bq] = gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, bq)); }
+  } else {            // one class of 2^m: its own batch, "next" in the same batch (G = 2) or in the class + 2 batch
+    const u32 G = 1u << dom.m;
+    a.logm = logn + 1 - dom.m; a.nseg = 1; a.npoints = size_t(1) << a.logm;
+    a.trace = dom.trace; a.trace_next = dom.trace_next; a.trace_stride = a.npoints;
+    a.zs = dom.zs; a.zs_next = dom.zs_next; a.zs_stride = a.npoints;
+    a.next_shift = G == 2 ? 1 : (dom.sigma + 2 >= G ? 1 : 0);
+    a.seg_off[0] = 0; a.seg_shift[0] = gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, dom.sigma));
+  }
+  a.wpow = get_ntt_tables(ctx, a.logm).w_fwd; a.w_inv = gl_inv(gl_root_of_unity(logn));
+  // Lagrange selectors on the evaluation points
   const NttTables& tb = get_ntt_tables(ctx, logn);
-  // Lagrange selectors on the LDE cosets
-  DevBuf<u64> lag_coeffs(ctx, 2 * N), lag_lde(ctx, 2 * L);
+  DevBuf<u64> lag_coeffs(ctx, 2 * N), lag_lde(ctx, dom.m == 0 ? 2 * L : 2 * a.npoints);
   u64 ninv = gl_inv((u64)N);
   k_fill_lagrange_coeffs<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(lag_coeffs, tb.w_fwd, ninv, N);
   LAUNCH_CHECK(ctx);
-  lde_columns(ctx, lag_coeffs, lag_lde, 2, logn, rate_bits);
-
-  DevBuf<u64> acc(ctx, (size_t)SBN_MAX_CHALLENGES * 2 * N);
-  QArgs a; memset(&a, 0, sizeof a);
-  a.trace = trace_lde; a.trace_stride = L; a.zs = zs_lde; a.zs_stride = L; a.logn = logn;
-  u64 w2n = gl_root_of_unity(logn + 1);
-  for (int bq = 0; bq < 2; bq++) { a.coset_off[bq] = (size_t)bq * step * N; a.coset_shift[bq] = gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, bq)); }
-  a.wpow = tb.w_fwd; a.w_inv = gl_inv(gl_root_of_unity(logn));
-  a.lagrange = lag_lde; a.lagrange_stride = L; a.pi = d_public_inputs; a.acc = acc;
+  if (dom.m == 0) { lde_columns(ctx, lag_coeffs, lag_lde, 2, logn, rate_bits); a.lagrange_stride = L; }
+  else { lde_class(ctx, lag_coeffs, lag_lde, 2, logn, 1, dom.m, dom.sigma); a.lagrange_stride = a.npoints; }
+  a.lagrange = lag_lde; a.pi = d_public_inputs; a.acc = d_acc;
   for (int c = 0; c < SBN_MAX_CHALLENGES; c++) a.alpha[c] = c < num_challenges ? alphas[c] : 0;
   DevBuf<u32> d_lhs, d_rhs; DevBuf<u64> d_gamma;
   std::vector<Segment> segs = air.segments;
@@ -242,10 +252,10 @@ void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_
     segs.push_back({SEG_PERMUTATION, 0, 0, 0, 0, 2 * perm.nz()});
   }
   DevBuf<u64> scratch, pi_lde;
-  a.pi_lde = acc; a.pi_per_chal = 0;   // valid pointer for AIRs without a public-input block (never dereferenced there)
+  a.pi_lde = d_acc; a.pi_per_chal = 0;   // valid pointer for AIRs without a public-input block (never dereferenced there)
   for (const Segment& s : segs)
-    if (s.kind == SEG_FQ_CORE || s.kind == SEG_G1_CORE || s.kind == SEG_G2_CORE || s.kind == SEG_FQ12_CORE) build_pi_binding(ctx, a, s, d_public_inputs, num_challenges, pi_lde);
-  for (const Segment& s : segs) if (s.kind == SEG_FQ12_MUL && !scratch.p) scratch = DevBuf<u64>(ctx, (size_t)12 * 31 * 2 * N);
+    if (s.kind == SEG_FQ_CORE || s.kind == SEG_G1_CORE || s.kind == SEG_G2_CORE || s.kind == SEG_FQ12_CORE) build_pi_binding(ctx, a, dom, s, d_public_inputs, num_challenges, pi_lde);
+  for (const Segment& s : segs) if (s.kind == SEG_FQ12_MUL && !scratch.p) scratch = DevBuf<u64>(ctx, (size_t)12 * 31 * a.npoints);
   a.scratch = scratch.p;
   bool first = true;
   for (const Segment& s : segs) {
@@ -254,21 +264,33 @@ void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_
     launch_segment(ctx, a, s);
     first = false;
   }
-  // divide by Z_H(x) = x^N - 1 = g^N (-1)^bq - 1
-  u64 gn = gl_exp_pow2(GL_MULT_GENERATOR, logn);
-  u64 zh0 = gl_inv(gl_sub(gn, 1)), zh1 = gl_inv(gl_sub(gl_neg(gn), 1));
-  size_t tot = 2 * N * num_challenges;
-  k_scale_cosets<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(acc, logn, num_challenges, zh0, zh1);
+  // divide by Z_H(x) = x^N - 1, constant on a segment: (seg_shift w_M^k)^N = seg_shift^N
+  u64 zh[2] = {0, 0};
+  for (int sg = 0; sg < a.nseg; sg++) zh[sg] = gl_inv(gl_sub(gl_exp_pow2(a.seg_shift[sg], logn), 1));
+  size_t tot = a.npoints * num_challenges;
+  k_scale_cosets<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(d_acc, a.logm, a.npoints, num_challenges, zh[0], zh[1]);
   LAUNCH_CHECK(ctx);
-  // per-coset interpolation (coset_ifft restricted to each half), then split into the two chunks
+}
+
+// per-coset interpolation (coset_ifft restricted to each half), then split into the two chunks
+void quotient_finish(sbn_ctx* ctx, const u64* d_acc, int num_challenges, int logn, u64* out_chunks) {
+  const size_t N = size_t(1) << logn;
+  const u64 w2n = gl_root_of_unity(logn + 1), gn = gl_exp_pow2(GL_MULT_GENERATOR, logn);
   DevBuf<u64> u(ctx, 2 * N);
   u64 inv2 = gl_inv(2), inv2gn = gl_inv(gl_mul(2, gn));
   for (int c = 0; c < num_challenges; c++) {
     for (int bq = 0; bq < 2; bq++) {
-      const u64* post = get_pow_table(ctx, gl_inv(a.coset_shift[bq]), logn);
-      ntt_batch(ctx, acc + ((size_t)c * 2 + bq) * N, N, u + (size_t)bq * N, N, 1, logn, true, 0, post);
+      const u64* post = get_pow_table(ctx, gl_inv(gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, bq))), logn);
+      ntt_batch(ctx, d_acc + ((size_t)c * 2 + bq) * N, N, u + (size_t)bq * N, N, 1, logn, true, 0, post);
     }
     k_quotient_split<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(u, u + N, out_chunks + (size_t)(2 * c) * N, out_chunks + (size_t)(2 * c + 1) * N, inv2, inv2gn, N);
     LAUNCH_CHECK(ctx);
   }
+}
+
+void compute_quotient_chunks(sbn_ctx* ctx, const AirDesc& air, const u64* trace_lde, const u64* zs_lde, const PermInstances& perm,
+                             const u64* d_public_inputs, const u64* alphas, int num_challenges, int logn, int rate_bits, u64* out_chunks) {
+  DevBuf<u64> acc(ctx, (size_t)SBN_MAX_CHALLENGES * (size_t(2) << logn));
+  quotient_eval(ctx, air, QDomain(), trace_lde, zs_lde, perm, d_public_inputs, alphas, num_challenges, logn, rate_bits, acc);
+  quotient_finish(ctx, acc, num_challenges, logn, out_chunks);
 }

@@ -3,8 +3,13 @@
 Proofs share no state (every `XExpStark` is a `Copy` value: reference src/curves/g1/exp.rs:232), so the
 data path needs no collective: rank r proves the batches `assign(num_batches, world, r)` on its own GPU.
 `torch.distributed` is used only for plumbing -- the max-over-ranks timing reduce and the gather of proof
-digests / lengths on rank 0 (NCCL on the GPU box, gloo in the CPU tests)."""
+digests / lengths on rank 0 (NCCL on the GPU box, gloo in the CPU tests).
+
+Intra-proof sharding (`prove_sharded`): the ranks of a group compute ONE proof together; the only exchanges
+are all-gathers of Merkle cap digests, quotient values and opened rows.  `dist_allgather` runs them over torch.distributed
+(NCCL between GPUs, gloo on CPU); `ThreadGroup` is the in-process version for ranks simulated as threads on one GPU."""
 import hashlib
+import threading
 
 import torch
 import torch.distributed as dist
@@ -39,3 +44,51 @@ def gather_digests(local, num_batches, device="cpu"):
         d = b"".join(int(buf[b, k]).to_bytes(8, "little", signed=True) for k in range(4))
         out.append((d.hex(), int(buf[b, 4])))
     return out
+
+
+def dist_allgather(group=None, device=None):
+    """all-gather of equal-length byte strings over torch.distributed for `prove_sharded`: `device` = the rank's CUDA device
+    under NCCL (the bytes are staged through a device tensor so the transfer runs over NVLink), None under gloo."""
+    world = dist.get_world_size(group)
+
+    def allgather(data):
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(world * len(data), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        raw = out.cpu().numpy().tobytes()
+        return [raw[i * len(data):(i + 1) * len(data)] for i in range(world)]
+
+    return allgather
+
+
+class ThreadGroup:
+    """In-process exchange for `world` ranks running as threads (one sbn context each, same or different GPUs)."""
+
+    def __init__(self, world):
+        self.world = world
+        self.slots = [None] * world
+        self.barrier = threading.Barrier(world)
+
+    def allgather(self, rank):
+        def fn(data):
+            self.slots[rank] = data
+            self.barrier.wait(timeout=600)
+            parts = list(self.slots)
+            self.barrier.wait(timeout=600)   # nobody overwrites a slot before everyone has read it
+            return parts
+        return fn
+
+
+def lde_class_of_rank(rank, world):
+    """The LDE class (natural LDE index mod world) rank `rank` commits to: bit-reversal of the rank, because plonky2 stores
+    leaves in bit-reversed order and a rank owns a contiguous run of Merkle cap entries (prover.cu `Shard::rho`)."""
+    m = world.bit_length() - 1
+    return int(format(rank, "0%db" % m)[::-1], 2) if m else 0
+
+
+def owner_of_leaf(leaf_index, log_lde_size, world):
+    """Rank whose cap subtrees contain leaf `leaf_index` (a FRI query index) and the leaf's index inside that rank's class."""
+    m = world.bit_length() - 1
+    return leaf_index >> (log_lde_size - m), leaf_index & ((1 << (log_lde_size - m)) - 1)

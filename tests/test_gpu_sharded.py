@@ -1,0 +1,105 @@
+"""GPU tests (-m gpu) of intra-proof sharding (sbn_prove_sharded): `world` cooperating ranks -- here
+threads with one sbn context (CUDA stream) each on cuda:0, exchanging through sharding.ThreadGroup -- must return, on every
+rank, the byte-identical proof the unsharded prover returns (which the other GPU tests pin to the oracle and the goldens)."""
+import hashlib
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded(sbn, world, make):
+    """make(ctx) -> (stark, trace, public_inputs); returns the proof bytes of every rank."""
+    from starky_bn254_b200 import sharding
+    grp = sharding.ThreadGroup(world)
+    out, err = [None] * world, []
+
+    def run(rank):
+        ctx = None
+        try:
+            ctx = sbn.Context(0)
+            stark, trace, pi = make(ctx)
+            out[rank] = sbn.prove_sharded(stark, stark.config(), trace, pi, rank, world, grp.allgather(rank)).to_bytes()
+            trace.free()
+        except BaseException as e:
+            err.append((rank, e))
+            grp.barrier.abort()
+        finally:
+            if ctx is not None:
+                ctx.close()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not err, err
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8, 16])
+def test_modular_sharded_proof_is_byte_identical(ctx, sbn, orc, golden, world):
+    n = 512
+    ios = sbn.synthetic.modular_ios(n)
+
+    def make(c):
+        stark = sbn.ModularStark(n, c)
+        return stark, stark.generate_trace(ios), np.zeros(0, dtype=np.uint64)
+
+    stark, trace, pi = make(ctx)
+    want = sbn.prove(stark, stark.config(), trace, pi).to_bytes()
+    assert hashlib.sha256(want).hexdigest() == golden["modular_512"]["proof_sha256"]
+    for rank, got in enumerate(_sharded(sbn, world, make)):
+        assert got == want, (world, rank)
+    assert orc.Air(orc.AIR_MODULAR, n).verify(want) == (True, "")
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_g1_sharded_proof_matches_golden(sbn, golden, world):
+    """The G1 n = 128 proof (BASELINE config 2) from 2 and 8 ranks: same bytes as the committed golden of the oracle prover."""
+    n = 128
+    syn = sbn.synthetic
+    ios = syn.g1_exp_ios(n)
+
+    def make(c):
+        stark = sbn.G1ExpStark(n, c)
+        trace = stark.generate_trace(ios)
+        full = syn.fill_g1_outputs(ios, trace.results())
+        return stark, trace, stark.generate_public_inputs(full)
+
+    for rank, got in enumerate(_sharded(sbn, world, make)):
+        assert len(got) == golden["g1_128"]["proof_len"], (world, rank)
+        assert hashlib.sha256(got).hexdigest() == golden["g1_128"]["proof_sha256"], (world, rank)
+
+
+def test_fq12_sharded_proof_is_byte_identical(ctx, sbn):
+    """Fq12 (the wide AIR: Fq12 products through the scratch batch, split range checks, 584 public inputs per instance)."""
+    n = 2
+    syn = sbn.synthetic
+    ios = syn.fq12_exp_ios(n)
+
+    def make(c):
+        stark = sbn.Fq12ExpStark(n, c)
+        trace = stark.generate_trace(ios)
+        full = syn.fill_outputs(ios, trace.results(), stark.io_size, stark.io_size - 8 * stark.result_words)
+        return stark, trace, stark.generate_public_inputs(full)
+
+    stark, trace, pi = make(ctx)
+    want = sbn.prove(stark, stark.config(), trace, pi).to_bytes()
+    for world in (2, 4):
+        for rank, got in enumerate(_sharded(sbn, world, make)):
+            assert got == want, (world, rank)
+
+
+def test_sharded_argument_errors(ctx, sbn):
+    n = 512
+    stark = sbn.ModularStark(n, ctx)
+    trace = stark.generate_trace(sbn.synthetic.modular_ios(n))
+    cfg = stark.config(); cfg.rate_bits = 2
+    with pytest.raises(sbn.SbnError, match="rate_bits = 1"):
+        sbn.prove_sharded(stark, cfg, trace, np.zeros(0, dtype=np.uint64), 0, 2, lambda b: [b, b])
+    with pytest.raises(sbn.SbnError, match="bad shard"):
+        sbn.prove_sharded(stark, stark.config(), trace, np.zeros(0, dtype=np.uint64), 0, 3, lambda b: [b, b, b])
+    # world = 1 is the plain prover (the callback is never used)
+    one = sbn.prove_sharded(stark, stark.config(), trace, np.zeros(0, dtype=np.uint64), 0, 1, None).to_bytes()
+    assert one == sbn.prove(stark, stark.config(), trace, np.zeros(0, dtype=np.uint64)).to_bytes()

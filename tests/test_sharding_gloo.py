@@ -50,3 +50,70 @@ def test_round_robin_sharding_and_gather(world, num_batches):
         covered += mine
     assert sorted(covered) == list(range(num_batches))          # no batch lost or proved twice
     assert len({r[4] for r in res}) == world                    # ranks draw distinct synthetic inputs
+
+
+def _allgather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.load_package()
+    from starky_bn254_b200 import sharding
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    ag = sharding.dist_allgather()
+    out = []
+    for size in (32, 4096, 100001):          # cap digests, a mid-size block, an odd length
+        parts = ag(bytes((rank * 7 + i) % 251 for i in range(size)))
+        out.append([hashlib.sha256(x).hexdigest() for x in parts])
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, out))
+
+
+def test_dist_allgather_bytes_gloo():
+    """The exchange `prove_sharded` runs between ranks (cap digests, quotient values, opened rows), over gloo."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40)
+    procs = [ctx.Process(target=_allgather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k, size in enumerate((32, 4096, 100001)):
+        want = [hashlib.sha256(bytes((r * 7 + i) % 251 for i in range(size))).hexdigest() for r in range(world)]
+        for rank, out in res:
+            assert out[k] == want
+
+
+def test_thread_group_and_class_ownership():
+    """Rank <-> LDE class <-> Merkle cap entries <-> query ownership, against the bit-reversal definition (prover.cu Shard)."""
+    import threading
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    from starky_bn254_b200 import sharding
+    rev = lambda x, bits: int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+    log_l, cap_height = 9, 4
+    for world in (1, 2, 4, 8, 16):
+        m = world.bit_length() - 1
+        seen = set()
+        for leaf in range(1 << log_l):
+            owner, local = sharding.owner_of_leaf(leaf, log_l, world)
+            i = rev(leaf, log_l)                                      # natural LDE index of the leaf
+            assert i % world == sharding.lde_class_of_rank(owner, world)
+            assert i // world == rev(local, log_l - m)                # position inside the class = local bit reversal
+            assert (leaf >> (log_l - cap_height)) >> (cap_height - m) == owner   # its cap entry belongs to the owner
+            seen.add((owner, local))
+        assert len(seen) == 1 << log_l
+    grp = sharding.ThreadGroup(4)
+    got = [None] * 4
+    def run(r):
+        ag = grp.allgather(r)
+        got[r] = [ag(b"a%d" % r), ag(b"b%d" % r)]
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    for r in range(4):
+        assert got[r] == [[b"a0", b"a1", b"a2", b"a3"], [b"b0", b"b1", b"b2", b"b3"]]
