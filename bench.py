@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--air", default="g1", choices=sorted(AIRS))
+    ap.add_argument("--no-intra-proof", action="store_true", help="skip the sharded single-proof latency measurement at N > 1")
     ap.add_argument("--inflight", type=int, default=4, help="independent proofs in flight per GPU (one context + CUDA stream each)")
     args = ap.parse_args()
     select_air(args.air)
@@ -133,6 +134,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -254,6 +259,39 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
 
+    # ---- latency mode: ONE proof computed by all ranks together (sbn_prove_sharded); the exchanges (cap digests,
+    # quotient values, opened rows) are NCCL all-gathers.  Reported beside the throughput number, not instead of it. ----
+    intra = None
+    if world > 1 and world in (2, 4, 8, 16) and not args.no_intra_proof:
+        ag = sharding.dist_allgather(device=torch.device("cuda", local))
+        raw0 = gen_ios(NUM_IO, seed=0x5EED0001)          # the same inputs on every rank: the trace is replicated
+
+        def step_sharded(single=False):
+            tr = stark.generate_trace(raw0)
+            ios = syn.fill_outputs(raw0, tr.results(), stark.io_size, out_off)
+            pi = stark.generate_public_inputs(ios)
+            p = sbn.prove(stark, cfg, tr, pi) if single else sbn.prove_sharded(stark, cfg, tr, pi, rank, world, ag)
+            tr.free()
+            return p.to_bytes()
+        for _ in range(2):
+            sharded_bytes = step_sharded()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        nsh = 4
+        for _ in range(nsh):
+            sharded_bytes = step_sharded()
+        s1.record(stream)
+        barrier()
+        sh_ms = sharding.max_over_ranks([s0.elapsed_time(s1) / nsh], device="cuda")[0]
+        import hashlib
+        same = sharding.gather_digests({rank: sharded_bytes}, world, device="cuda")
+        ok = len({d[0] for d in same}) == 1
+        if rank == 0:
+            ok = ok and hashlib.sha256(step_sharded(single=True)).hexdigest() == same[0][0]
+        intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok,
+                 "collectives": "3 commitments x all_gather(cap digests) + all_gather(quotient values) + all_gather(opened rows), NCCL"}
+
     ms_total, e2e_ms = sharding.max_over_ranks([ms_total, e2e_s * 1000.0], device="cuda")
     # the only other cross-rank traffic: digests of the last proof of every rank (the "gather" of SURVEY §8e)
     digests = sharding.gather_digests({rank: last_proof_bytes}, world, device="cuda")
@@ -303,6 +341,7 @@ def main():
                      "warp_instr_per_perm": 29.3e3 / 32,
                      "issue_frac": (perms_per_proof * ksteps / (leaf["ms"] / 1e3) * 29.3e3 / 32) / (148 * 4 * 1965e6) if leaf["ms"] else None},
         "serial_ms_per_step": serial_ms_per_step,
+        "intra_proof": intra,
         "kernel_ms_per_proof": {k: round(v["ms"] / ksteps, 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
         "phase_ms_last_proof": {k: round(v, 3) for k, v in phases.items()},
     }
@@ -313,7 +352,8 @@ def main():
         line["cpu_baseline"] = {"value": 1000.0 / full_ms, "unit": "proofs/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "oracle (C++/OpenMP restatement, not the Rust binary): heavy phases on 1/%d of their columns/instances/points scaled x%d, "
                                           "FRI tail in full; %.1f s of CPU wall; est. full-proof phases ms=%s" % (1 << SAMPLE_SHIFT, 1 << SAMPLE_SHIFT, wall, {k: round(v, 1) for k, v in est.items()})}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
