@@ -56,8 +56,8 @@ HD u64 gl_from_i64(long long x) { return x >= 0 ? (u64)x : GL_P - (u64)(-x); }
 // (x3:x2:x1:x0) mod p as an arbitrary 64-bit representative, using 2^64 = 2^32 - 1 and 2^96 = -1:
 //   T = (x1:x0) - (x2 + x3) + x2 * 2^32  lies in (-2^33, 2^65 - 2^33]; its 64-bit wrap count d in {-1, 0, 1} is the
 //   carry of the addition plus the (negative) borrow of the subtraction, and T - d * 2^64 + d * (2^32 - 1) cannot wrap again.
-// 11 instructions; the 128-bit product itself is left to the compiler (3 IMAD.WIDE + 1 IMAD.WIDE.X).
-__device__ __forceinline__ u64 gl_reduce128_nc(u64 lo, u64 hi) {
+// 11 instructions; the product comes as words from gl_mul128_words / gl_sqr128_words below.
+__device__ __forceinline__ u64 gl_reduce_words_nc(u32 x0, u32 x1, u32 x2, u32 x3) {
   u32 r0, r1;
   asm("{\n\t"
       ".reg .u32 s, cs, b, d, e, f;\n\t"
@@ -74,11 +74,59 @@ __device__ __forceinline__ u64 gl_reduce128_nc(u64 lo, u64 hi) {
       "addc.u32 %1, %1, f;\n\t"
       "}"
       : "=&r"(r0), "=&r"(r1)
-      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
   return ((u64)r1 << 32) | r0;
 }
+__device__ __forceinline__ u64 gl_reduce128_nc(u64 lo, u64 hi) { return gl_reduce_words_nc((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)); }
+// 128-bit product as four 32-bit words from exactly four 32 x 32 -> 64 multiplications (IMAD.WIDE) and five carry adds.  The
+// compiler's `a * b` + `__umul64hi(a, b)` pair costs five IMAD.WIDE and two IMAD (it forms the low product twice), i.e.
+// 24 cycles of the multiplier pipe per product against 16 here (tools/microbench: IMAD 2 cycles, IMAD.WIDE 4 per warp).
+__device__ __forceinline__ void gl_mul128_words(u64 a, u64 b, u32& x0, u32& x1, u32& x2, u32& x3) {
+  asm("{\n\t"
+      ".reg .u64 p, q, r, s;\n\t"
+      ".reg .u32 ph, ql, qh, rl, rh, sl, sh;\n\t"
+      "mul.wide.u32 p, %4, %6;\n\t"     // a_lo b_lo
+      "mul.wide.u32 q, %4, %7;\n\t"     // a_lo b_hi
+      "mul.wide.u32 r, %5, %6;\n\t"     // a_hi b_lo
+      "mul.wide.u32 s, %5, %7;\n\t"     // a_hi b_hi
+      "mov.b64 {%0, ph}, p;\n\t"
+      "mov.b64 {ql, qh}, q;\n\t"
+      "mov.b64 {rl, rh}, r;\n\t"
+      "mov.b64 {sl, sh}, s;\n\t"
+      "add.cc.u32 %1, ph, ql;\n\t"
+      "addc.cc.u32 %2, qh, sl;\n\t"
+      "addc.u32 %3, sh, 0;\n\t"
+      "add.cc.u32 %1, %1, rl;\n\t"
+      "addc.cc.u32 %2, %2, rh;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "}"
+      : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)       // every input is consumed by the four multiplications before an output is written
+      : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+}
+// a^2: three multiplications, the cross product doubled by a funnel shift.
+__device__ __forceinline__ void gl_sqr128_words(u64 a, u32& x0, u32& x1, u32& x2, u32& x3) {
+  asm("{\n\t"
+      ".reg .u64 p, q, s;\n\t"
+      ".reg .u32 ph, ql, qh, sl, sh, d0, d1, d2;\n\t"
+      "mul.wide.u32 p, %4, %4;\n\t"     // a_lo^2
+      "mul.wide.u32 q, %4, %5;\n\t"     // a_lo a_hi
+      "mul.wide.u32 s, %5, %5;\n\t"     // a_hi^2
+      "mov.b64 {%0, ph}, p;\n\t"
+      "mov.b64 {ql, qh}, q;\n\t"
+      "mov.b64 {sl, sh}, s;\n\t"
+      "shl.b32 d0, ql, 1;\n\t"                   // 2 q = d2:d1:d0
+      "shf.l.clamp.b32 d1, ql, qh, 1;\n\t"
+      "shr.u32 d2, qh, 31;\n\t"
+      "add.cc.u32 %1, ph, d0;\n\t"
+      "addc.cc.u32 %2, sl, d1;\n\t"
+      "addc.u32 %3, sh, d2;\n\t"
+      "}"
+      : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+      : "r"((u32)a), "r"((u32)(a >> 32)));
+}
 // a * b mod p as an arbitrary 64-bit representative; a, b arbitrary u64.
-__device__ __forceinline__ u64 gl_mul_nc(u64 a, u64 b) { return gl_reduce128_nc(a * b, __umul64hi(a, b)); }
+__device__ __forceinline__ u64 gl_mul_nc(u64 a, u64 b) { u32 x0, x1, x2, x3; gl_mul128_words(a, b, x0, x1, x2, x3); return gl_reduce_words_nc(x0, x1, x2, x3); }
+__device__ __forceinline__ u64 gl_sqr_nc(u64 a) { u32 x0, x1, x2, x3; gl_sqr128_words(a, x0, x1, x2, x3); return gl_reduce_words_nc(x0, x1, x2, x3); }
 // a + b mod p, a arbitrary u64, b canonical (< p); result arbitrary u64 representative.
 __device__ __forceinline__ u64 gl_add_nc(u64 a, u64 b) {
   u32 r0, r1;

@@ -53,7 +53,7 @@ static __constant__ u64 d_poseidon_fast[639] = {
 
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ u64 poseidon_sbox_nc(u64 x) {
-  u64 x2 = gl_mul_nc(x, x), x3 = gl_mul_nc(x2, x), x4 = gl_mul_nc(x2, x2);
+  u64 x2 = gl_sqr_nc(x), x3 = gl_mul_nc(x2, x), x4 = gl_sqr_nc(x2);
   return gl_mul_nc(x3, x4);
 }
 // s <- MDS * s + rc[rc_off ..] (the next round's constants; offset 360 = zeros), lanes arbitrary u64 in and out.
