@@ -120,10 +120,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--air", default="g1", choices=sorted(AIRS))
+    ap.add_argument("--num-io", type=int, default=0, help="instances per proof (power of two; default: the AIR's headline size)")
     ap.add_argument("--no-intra-proof", action="store_true", help="skip the sharded single-proof latency measurement at N > 1")
-    ap.add_argument("--inflight", type=int, default=4, help="independent proofs in flight per GPU (one context + CUDA stream each)")
+    ap.add_argument("--inflight", type=int, default=6, help="independent proofs in flight per GPU (one context + CUDA stream each)")
     args = ap.parse_args()
     select_air(args.air)
+    if args.num_io:
+        global NUM_IO, WORKLOAD
+        WORKLOAD = WORKLOAD.replace("num_io=%d:" % NUM_IO, "num_io=%d (non-default size; row / column counts in this text are those of the default):" % args.num_io)
+        NUM_IO = args.num_io
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -335,7 +340,7 @@ def main():
                      "traffic": 1.7712e9 if AIR == "g1" else None,
                      "traffic_note": "largest of the 3 launches per proof (trace commitment); `achieved` averages all 3 (trace, Z, quotient commitments)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "note": "kernel is bound by the integer multiplier (FMA-heavy) pipe, 86 % busy under ncu (Poseidon ~ 2.5e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
+                     "note": "kernel is bound by the integer multiplier (FMA-heavy) pipe, 86 %% busy under ncu (Poseidon ~ 2.5e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
                      "share_of_kernel_time": leaf["ms"] / total_kernel_ms if total_kernel_ms else None},
         # integer-pipe view of the same kernel: ncu counts 770 warp instructions per permutation for this build (21.2 G warp
         # instructions / 27.5 M permutations, profiles/r01_leaf_hash_ncu_summary_dp2a.txt); issue peak = 148 SMs x 4 schedulers x

@@ -264,11 +264,13 @@ __global__ void k_ntt_small(const u64* __restrict__ in, size_t in_stride, u64* _
   }
 }
 
+// shared memory of a pass with sub-transform size 2^l: the tile (row stride T + 1) and the 2^l twiddles; 131 KB at l = 12
+static constexpr int ntt_tile_bytes(int l) { return (int)((((size_t)1 << l) * (((size_t)1 << ntt_logT_of(l)) + (ntt_logT_of(l) > 0 ? 1 : 0)) + ((size_t)1 << l)) * 8); }
 template <int L> static void launch_pass1(sbn_ctx* ctx, dim3 grid, size_t smem, bool pre, const u64* in, size_t in_stride, u64* tmp, const u64* W, const u64* F, const u64* P1, int l2) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_tile_bytes(L)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_tile_bytes(L)));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
@@ -279,7 +281,7 @@ template <int L> static void launch_pass1(sbn_ctx* ctx, dim3 grid, size_t smem, 
 template <int L> static void launch_pass2(sbn_ctx* ctx, dim3 grid, size_t smem, const u64* tmp, u64* out, size_t out_stride, const u64* W, const u64* postscale, int l1) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_tile_bytes(L)));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
@@ -314,8 +316,7 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
   const int logT1 = ntt_logT_of(l1), logT2 = ntt_logT_of(l2);
   const u64* F = get_fourstep_table(ctx, logn, inverse, pre_base);
   const u64* P1 = pre_base ? get_pow_table(ctx, gl_exp_pow2(pre_base, l2), l1) : nullptr;   // (c^N2)^n1
-  auto tile_bytes = [](int l, int logT) { return ((size_t(1) << l) * ((size_t(1) << logT) + (logT > 0 ? 1 : 0)) + (size_t(1) << l)) * 8; };
-  size_t smem1 = tile_bytes(l1, logT1), smem2 = tile_bytes(l2, logT2);
+  size_t smem1 = ntt_tile_bytes(l1), smem2 = ntt_tile_bytes(l2);
   // Column chunks sized so the intermediate stays L2-resident between the two passes.
   size_t chunk = (size_t(48) << 20) / (N * 8);
   if (chunk < 1) chunk = 1;

@@ -67,6 +67,26 @@ def test_commit_linearity_large(ctx):
         assert acc == int(ls[0][i])
 
 
+@pytest.mark.parametrize("logn,points", [(21, ((0, 0), (0, 5), (1, 3), (1, (1 << 22) - 1))), (23, ((0, 1), (1, (1 << 24) - 2)))])
+def test_ntt_largest_tiles(ctx, logn, points):
+    """The two-pass NTT at its largest sub-transform sizes (2^23 = 2^11 x 2^12, 131 KB of shared memory per block: the FRI
+    codeword of config 5 at 2^20 rows and rate 8), checked by direct polynomial evaluation: the coefficients returned for random
+    values must reproduce those values on the subgroup (kind 0) and the LDE on the coset 7<w_2N> (kind 1)."""
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    v = rng.integers(0, P, size=(1, n), dtype=np.uint64)
+    cf, lde, _ = ctx.commit_columns(v, 1, 4)
+    coeffs = [int(c) for c in cf[0][::-1]]
+    w = pow(1753635133440165772, 1 << (32 - logn), P)
+    wl = pow(1753635133440165772, 1 << (32 - logn - 1), P)
+    for kind, i in points:
+        x = pow(w, i, P) if kind == 0 else 7 * pow(wl, i, P) % P
+        acc = 0
+        for c in coeffs:
+            acc = (acc * x + c) % P
+        assert acc == int(v[0][i] if kind == 0 else lde[0][i]), (kind, i)
+
+
 @pytest.mark.parametrize("n", [256, 512, 4096])
 def test_modular_trace_matches_oracle(ctx, sbn, orc, n):
     ios = sbn.synthetic.modular_ios(n, seed=1000 + n)
