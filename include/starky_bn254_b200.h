@@ -34,7 +34,9 @@ enum {
   SBN_AIR_G1_EXP = 2,       /* G1ExpStark          src/curves/g1/exp.rs:232-742 */
   SBN_AIR_G2_EXP = 3,       /* G2ExpStark          src/curves/g2/exp.rs */
   SBN_AIR_FQ12_EXP = 4,     /* Fq12ExpStark        src/fields/fq12/exp.rs */
-  SBN_AIR_FQ12_EXP_U64 = 5  /* Fq12ExpU64Stark     src/fields/fq12_u64/exp_u64.rs */
+  SBN_AIR_FQ12_EXP_U64 = 5, /* Fq12ExpU64Stark     src/fields/fq12_u64/exp_u64.rs */
+  SBN_AIR_G1_MULADD = 6,    /* G1Stark (gadget test AIR)   src/curves/g1/muladd.rs:462-624 (num_io = rows, one addition per row) */
+  SBN_AIR_FQ12_MUL = 7      /* Fq12Stark (gadget test AIR) src/fields/fq12/mul.rs:355-484  (num_io = rows, one product per row) */
 };
 
 #define SBN_OK 0
@@ -61,6 +63,10 @@ typedef struct { uint64_t x[16], offset[16]; uint32_t exp_val[8]; uint64_t outpu
 typedef struct { uint64_t x[48], offset[48]; uint32_t exp_val[8]; uint64_t output[48]; } sbn_fq12_exp_io;
 /* Input record of Fq12ExpU64Stark, replaces `Fq12ExpU64IONative` (src/fields/fq12_u64/exp_u64.rs:85-90); exp_val < 2^64 - 2^32 + 1. */
 typedef struct { uint64_t x[48], offset[48]; uint64_t exp_val; uint64_t output[48]; } sbn_fq12_exp_u64_io;
+/* Input record of G1Stark: one row = the two affine points it adds, a.x != b.x (src/curves/g1/muladd.rs:486-492). */
+typedef struct { uint64_t a_x[4], a_y[4], b_x[4], b_y[4]; } sbn_g1_muladd_io;
+/* Input record of Fq12Stark: one row = the two Fq12 elements it multiplies, flat MyFq12 order (src/fields/fq12/mul.rs:381-386). */
+typedef struct { uint64_t x[48], y[48]; } sbn_fq12_mul_io;
 /* Input record of ModularStark: one row = two canonical Fq residues (src/modular/modular.rs:385-390). */
 typedef struct { uint64_t input0[4], input1[4]; } sbn_modular_io;
 

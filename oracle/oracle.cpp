@@ -8,6 +8,7 @@
 #include "air_g1.hpp"
 #include "air_g2.hpp"
 #include "air_fq12.hpp"
+#include "air_gadgets.hpp"
 #include "sample.hpp"
 #include <cstdio>
 #include <omp.h>
@@ -18,7 +19,7 @@
 using namespace orc;
 namespace orc { FieldParams g_field; }
 
-enum { AIR_MODULAR = 0, AIR_FQ_EXP = 1, AIR_G1_EXP = 2, AIR_G2_EXP = 3, AIR_FQ12_EXP = 4, AIR_FQ12_EXP_U64 = 5 };
+enum { AIR_MODULAR = 0, AIR_FQ_EXP = 1, AIR_G1_EXP = 2, AIR_G2_EXP = 3, AIR_FQ12_EXP = 4, AIR_FQ12_EXP_U64 = 5, AIR_G1_MULADD = 6, AIR_FQ12_MUL = 7 };
 
 struct OrcConfig { uint32_t security_bits, num_challenges, rate_bits, cap_height, pow_bits, fri_arity_bits, fri_final_poly_bits, num_query_rounds; uint64_t coset_shift; };
 static StarkConfig to_cfg(const OrcConfig* c) {
@@ -85,6 +86,8 @@ void* orc_air_create(int id, size_t num_io) {
     case AIR_G2_EXP: h->air.reset(new G2ExpStark(num_io)); break;
     case AIR_FQ12_EXP: h->air.reset(new Fq12ExpStark(num_io)); break;
     case AIR_FQ12_EXP_U64: h->air.reset(new Fq12ExpU64Stark(num_io)); break;
+    case AIR_G1_MULADD: h->air.reset(new G1Stark()); break;
+    case AIR_FQ12_MUL: h->air.reset(new Fq12Stark()); break;
     default: delete h; g_err = "unsupported air"; return nullptr;
   }
   return h;
@@ -92,10 +95,10 @@ void* orc_air_create(int id, size_t num_io) {
 void orc_air_destroy(void* p) { delete (AirHandle*)p; }
 size_t orc_air_num_columns(void* p) { return ((AirHandle*)p)->air->num_columns(); }
 size_t orc_air_num_public_inputs(void* p) { return ((AirHandle*)p)->air->num_public_inputs(); }
-size_t orc_air_num_rows(void* p) { AirHandle* h = (AirHandle*)p; return h->id == AIR_MODULAR ? h->num_io : (h->id == AIR_FQ12_EXP_U64 ? 128 : 512) * h->num_io; }
+size_t orc_air_num_rows(void* p) { AirHandle* h = (AirHandle*)p; return (h->id == AIR_MODULAR || h->id == AIR_G1_MULADD || h->id == AIR_FQ12_MUL) ? h->num_io : (h->id == AIR_FQ12_EXP_U64 ? 128 : 512) * h->num_io; }
 size_t orc_air_num_permutation_pairs(void* p) { return ((AirHandle*)p)->air->permutation_pairs().size(); }
 size_t orc_air_result_words(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_FQ_EXP: return 4; case AIR_G1_EXP: return 8; case AIR_G2_EXP: return 16; case AIR_FQ12_EXP: case AIR_FQ12_EXP_U64: return 48; } return 0; }
-size_t orc_air_io_size(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_MODULAR: return 64; case AIR_G1_EXP: return sizeof(G1IoBlob); case AIR_FQ_EXP: return sizeof(FqIoBlob); case AIR_G2_EXP: return sizeof(G2IoBlob);
+size_t orc_air_io_size(void* p) { AirHandle* h = (AirHandle*)p; switch (h->id) { case AIR_MODULAR: return 64; case AIR_G1_MULADD: return 128; case AIR_FQ12_MUL: return 768; case AIR_G1_EXP: return sizeof(G1IoBlob); case AIR_FQ_EXP: return sizeof(FqIoBlob); case AIR_G2_EXP: return sizeof(G2IoBlob);
   case AIR_FQ12_EXP: return sizeof(Fq12IoBlob); case AIR_FQ12_EXP_U64: return sizeof(Fq12U64IoBlob); } return 0; }
 
 static std::vector<G1ExpIONative> g1_ios(const void* ios, size_t n) {
@@ -133,6 +136,14 @@ int orc_generate_trace(void* p, const void* ios, size_t num_io, u64* out_cols, u
       const u64* b = (const u64*)ios; std::vector<std::array<U256, 2>> in(num_io);
       for (size_t i = 0; i < num_io; i++) { in[i][0] = mk(b + 8 * i); in[i][1] = mk(b + 8 * i + 4); }
       cols = static_cast<ModularStark*>(h->air.get())->generate_trace(in);
+    } else if (h->id == AIR_G1_MULADD) {   // one record per row: a.x a.y b.x b.y
+      const u64* b = (const u64*)ios; std::vector<std::array<G1Point, 2>> in(num_io);
+      for (size_t i = 0; i < num_io; i++) { in[i][0] = {mk(b + 16 * i), mk(b + 16 * i + 4)}; in[i][1] = {mk(b + 16 * i + 8), mk(b + 16 * i + 12)}; }
+      cols = static_cast<G1Stark*>(h->air.get())->generate_trace(in);
+    } else if (h->id == AIR_FQ12_MUL) {    // one record per row: x[12] y[12]
+      const u64* b = (const u64*)ios; std::vector<std::array<Fq12Words, 2>> in(num_io);
+      for (size_t i = 0; i < num_io; i++) { in[i][0] = mk12(b + 96 * i); in[i][1] = mk12(b + 96 * i + 48); }
+      cols = static_cast<Fq12Stark*>(h->air.get())->generate_trace(in);
     } else if (h->id == AIR_G1_EXP) {
       std::vector<G1Point> res;
       cols = static_cast<G1ExpStark*>(h->air.get())->generate_trace(g1_ios(ios, num_io), &res);
@@ -159,7 +170,7 @@ int orc_generate_trace(void* p, const void* ios, size_t num_io, u64* out_cols, u
 int orc_generate_public_inputs(void* p, const void* ios, size_t num_io, u64* out) {
   AirHandle* h = (AirHandle*)p;
   std::vector<GF> pi;
-  if (h->id == AIR_MODULAR) return 0;
+  if (h->id == AIR_MODULAR || h->id == AIR_G1_MULADD || h->id == AIR_FQ12_MUL) return 0;
   try {
   if (h->id == AIR_G1_EXP) pi = static_cast<G1ExpStark*>(h->air.get())->generate_public_inputs(g1_ios(ios, num_io));
   else if (h->id == AIR_FQ_EXP) pi = static_cast<FqExpStark*>(h->air.get())->generate_public_inputs(fq_ios(ios, num_io));

@@ -9,7 +9,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_DIR, "liboracle.so")
 
-AIR_MODULAR, AIR_FQ_EXP, AIR_G1_EXP, AIR_G2_EXP, AIR_FQ12_EXP, AIR_FQ12_EXP_U64 = range(6)
+AIR_MODULAR, AIR_FQ_EXP, AIR_G1_EXP, AIR_G2_EXP, AIR_FQ12_EXP, AIR_FQ12_EXP_U64, AIR_G1_MULADD, AIR_FQ12_MUL = range(8)
 
 
 class Config(C.Structure):

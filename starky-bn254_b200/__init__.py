@@ -18,7 +18,7 @@ from . import synthetic  # noqa: F401  (seeded inputs, shared by tests and bench
 _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libstarkybn254_b200.so")
 
-AIR_MODULAR, AIR_FQ_EXP, AIR_G1_EXP, AIR_G2_EXP, AIR_FQ12_EXP, AIR_FQ12_EXP_U64 = range(6)
+AIR_MODULAR, AIR_FQ_EXP, AIR_G1_EXP, AIR_G2_EXP, AIR_FQ12_EXP, AIR_FQ12_EXP_U64, AIR_G1_MULADD, AIR_FQ12_MUL = range(8)
 
 
 class SbnError(RuntimeError):
@@ -289,6 +289,18 @@ class _Stark:
 class ModularStark(_Stark):
     """reference src/modular/modular.rs:361-537 (rows = num_io)."""
     AIR = AIR_MODULAR
+
+
+class G1Stark(_Stark):
+    """The reference's gadget test AIR, one G1 addition per row: src/curves/g1/muladd.rs:462-624 (rows = num_io;
+    inputs: packed sbn_g1_muladd_io records)."""
+    AIR = AIR_G1_MULADD
+
+
+class Fq12Stark(_Stark):
+    """The reference's gadget test AIR, one Fq12 product per row: src/fields/fq12/mul.rs:355-484 (rows = num_io;
+    inputs: packed sbn_fq12_mul_io records)."""
+    AIR = AIR_FQ12_MUL
 
 
 class G1ExpStark(_Stark):

@@ -100,6 +100,25 @@ AirDesc make_air(int air_id, size_t num_io) {
       a.segments.push_back({SEG_SPLIT_RANGE_CHECK, (int)lookups, (int)t0, (int)nrc, 0, 5 * (size_t)nrc + 3});
       break;
     }
+    case SBN_AIR_G1_MULADD: {  // reference src/curves/g1/muladd.rs:462-468 (rows = num_io, a power of two >= 256)
+      const u32 MAIN = 24 * 16 + 2, T0 = 4 * 16, NT = 20 * 16 - 4;
+      SBN_REQUIRE((num_io & (num_io - 1)) == 0 && num_io >= 256, "G1Stark: rows must be a power of two >= 256");
+      a.num_columns = MAIN + 1 + 6 * NT; a.num_public_inputs = 0; a.num_rows = num_io; a.io_size = sizeof(sbn_g1_muladd_io); a.result_words = 0;
+      add_split_pairs(a, MAIN, NT);
+      a.segments.push_back({SEG_SPLIT_RANGE_CHECK, (int)MAIN, (int)T0, (int)NT, 0, 5 * (size_t)NT + 3});
+      a.segments.push_back({SEG_G1_ADD, 64, 384, 0, 0, 165});      // eval_g1_add(is_add, ...)       muladd.rs:579
+      a.segments.push_back({SEG_G1_DOUBLE, 64, 385, 0, 0, 165});   // eval_g1_double(is_double, ...) muladd.rs:580
+      break;
+    }
+    case SBN_AIR_FQ12_MUL: {   // reference src/fields/fq12/mul.rs:355-363 (rows = num_io, a power of two >= 256)
+      const u32 MAIN = 108 * 16 + 1, T0 = 24 * 16, NT = 84 * 16 - 12;
+      SBN_REQUIRE((num_io & (num_io - 1)) == 0 && num_io >= 256, "Fq12Stark: rows must be a power of two >= 256");
+      a.num_columns = MAIN + 1 + 6 * NT; a.num_public_inputs = 0; a.num_rows = num_io; a.io_size = sizeof(sbn_fq12_mul_io); a.result_words = 0;
+      add_split_pairs(a, MAIN, NT);
+      a.segments.push_back({SEG_SPLIT_RANGE_CHECK, (int)MAIN, (int)T0, (int)NT, 0, 5 * (size_t)NT + 3});
+      a.segments.push_back({SEG_FQ12_MUL, 108 * 16, 0, 0, 0, 12 * 66});   // eval_fq12_mul(filter, x, y)  mul.rs:447
+      break;
+    }
     default: throw SbnError(SBN_ERR_UNSUPPORTED, "unknown AIR identifier");
   }
   return a;

@@ -665,8 +665,69 @@ static void generate_modular(sbn_ctx* ctx, const AirDesc& air, const void* ios, 
   SBN_REQUIRE(!h_err, "ModularStark input is not a canonical Fq residue");
 }
 
+// ---------------- gadget test AIRs: G1Stark (one addition per row), Fq12Stark (one product per row) ----------------
+// main columns: a(32) b(32) G1Output(320) is_add is_double   (reference src/curves/g1/muladd.rs:481-546)
+__global__ void __launch_bounds__(128) k_g1_muladd_rows(const sbn_g1_muladd_io* __restrict__ ios, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  u32 ax[8], ay[8], bx[8], by[8];
+  u64x4_to_words((const u64*)ios[r].a_x, ax); u64x4_to_words((const u64*)ios[r].a_y, ay); u64x4_to_words((const u64*)ios[r].b_x, bx); u64x4_to_words((const u64*)ios[r].b_y, by);
+  if (fq_geq_p(ax) || fq_geq_p(ay) || fq_geq_p(bx) || fq_geq_p(by)) { *err = 2; return; }
+  ColWriter w{cols + r, N};
+  if (!g1_row(ax, ay, bx, by, G1_OP_ADD, w)) *err = 1;
+  w(384, 1); w(385, 0);
+}
+// main columns: x(192) y(192) Fq12Output(1344) filter   (reference src/fields/fq12/mul.rs:378-419).  Block = 32 rows x 12
+// coefficients; thread (row, oi) produces coefficient oi of the row's product and its reduction witness.
+__global__ void __launch_bounds__(384) k_fq12_mul_rows(const sbn_fq12_mul_io* __restrict__ ios, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
+  __shared__ unsigned short sx[32][192], sy[32][192];
+  __shared__ Fq mx[32][12], my[32][12];
+  const int lr = threadIdx.x & 31, oi = threadIdx.x >> 5;
+  const size_t r = blockIdx.x * (size_t)32 + lr;   // N is a multiple of 32
+  u32 xw[8], yw[8];
+  u64x4_to_words((const u64*)ios[r].x + 4 * oi, xw); u64x4_to_words((const u64*)ios[r].y + 4 * oi, yw);
+  if (fq_geq_p(xw) || fq_geq_p(yw)) *err = 2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    sx[lr][16 * oi + 2 * i] = xw[i] & 0xFFFF; sx[lr][16 * oi + 2 * i + 1] = xw[i] >> 16;
+    sy[lr][16 * oi + 2 * i] = yw[i] & 0xFFFF; sy[lr][16 * oi + 2 * i + 1] = yw[i] >> 16;
+  }
+  mx[lr][oi] = fq_from_words(xw); my[lr][oi] = fq_from_words(yw);
+  __syncthreads();
+  ColWriter w{cols + r, N};
+  write_limbs16(w, 16 * oi, xw); write_limbs16(w, 192 + 16 * oi, yw);
+  u32 ow[8];
+  fq_to_words(fq12_mul_coeff(mx[lr], my[lr], oi), ow);
+  fq12_row_coeff(sx[lr], sy[lr], ow, oi, EXP_OP_MUL, w);
+  if (oi == 0) w(108 * 16, 1);
+}
+static void generate_gadget(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool on_device, u64* d_cols) {
+  const size_t N = air.num_rows;
+  DevBuf<unsigned char> buf; const void* d_ios = ios;
+  if (!on_device) {
+    buf = DevBuf<unsigned char>(ctx, N * air.io_size);
+    CUDA_CHECK(cudaMemcpyAsync(buf, ios, N * air.io_size, cudaMemcpyHostToDevice, ctx->stream));
+    d_ios = buf;
+  }
+  DevBuf<int> err(ctx, 1);
+  CUDA_CHECK(cudaMemsetAsync(err, 0, 4, ctx->stream));
+  if (air.air_id == SBN_AIR_G1_MULADD) {
+    { KScope ks(ctx, "g1_muladd_rows"); k_g1_muladd_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((const sbn_g1_muladd_io*)d_ios, d_cols, N, err); LAUNCH_CHECK(ctx); }
+    generate_split_u16_range_check_cols(ctx, d_cols, N, 4 * 16, 20 * 16 - 4, 24 * 16 + 2);
+  } else {
+    { KScope ks(ctx, "fq12_mul_rows"); k_fq12_mul_rows<<<(unsigned)(N / 32), 384, 0, ctx->stream>>>((const sbn_fq12_mul_io*)d_ios, d_cols, N, err); LAUNCH_CHECK(ctx); }
+    generate_split_u16_range_check_cols(ctx, d_cols, N, 24 * 16, 84 * 16 - 12, 108 * 16 + 1);
+  }
+  int h_err = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  SBN_REQUIRE(h_err != 2, "gadget AIR input is not a canonical Fq residue");
+  SBN_REQUIRE(h_err != 1, "G1Stark: the two points of a row have equal x (the addition gadget divides by b.x - a.x)");
+}
+
 void generate_trace(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool ios_on_device, u64* d_cols, u64* h_results) {
   switch (air.air_id) {
+    case SBN_AIR_G1_MULADD: case SBN_AIR_FQ12_MUL: generate_gadget(ctx, air, ios, ios_on_device, d_cols); break;
     case SBN_AIR_MODULAR: generate_modular(ctx, air, ios, ios_on_device, d_cols); break;
     case SBN_AIR_G1_EXP: generate_g1(ctx, air, ios, ios_on_device, d_cols, h_results); break;
     case SBN_AIR_FQ_EXP: generate_fq(ctx, air, ios, ios_on_device, d_cols, h_results); break;
@@ -678,7 +739,7 @@ void generate_trace(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool ios_
 
 void format_public_inputs(const AirDesc& air, const void* ios, u64* out) {
   switch (air.air_id) {
-    case SBN_AIR_MODULAR: break;
+    case SBN_AIR_MODULAR: case SBN_AIR_G1_MULADD: case SBN_AIR_FQ12_MUL: break;
     case SBN_AIR_G1_EXP: {  // reference src/curves/g1/exp.rs:124-135: x.x x.y offset.x offset.y exp_val output.x output.y, 8 u32 limbs each
       const sbn_g1_exp_io* h = (const sbn_g1_exp_io*)ios;
       for (size_t i = 0; i < air.num_io; i++) {

@@ -56,6 +56,25 @@ def modular_ios(num_rows, seed=0x5EED0005):
 G1_IO_SIZE = 224
 
 
+def g1_muladd_ios(num_rows, seed=0x5EED0006, distinct=64):
+    """G1Stark rows (reference src/curves/g1/muladd.rs:486-492 draws two random points per row): a.x a.y b.x b.y.  Square roots
+    in pure Python are slow, so `distinct` random points are drawn once and paired pseudo-randomly (a != b in every row)."""
+    rng = SplitMix64(seed)
+    pts = [random_g1(rng) for _ in range(distinct)]
+    out = bytearray()
+    for _ in range(num_rows):
+        i = rng.below(distinct)
+        j = (i + 1 + rng.below(distinct - 1)) % distinct
+        out += _le32(pts[i][0]) + _le32(pts[i][1]) + _le32(pts[j][0]) + _le32(pts[j][1])
+    return bytes(out)
+
+
+def fq12_mul_ios(num_rows, seed=0x5EED0007):
+    """Fq12Stark rows (reference src/fields/fq12/mul.rs:381-382): x, y uniform in Fq12, 12 residues each (MyFq12 order)."""
+    rng = SplitMix64(seed)
+    return b"".join(_le32(rng.below(BN254_P)) for _ in range(24 * num_rows))
+
+
 def g1_exp_ios(num_io, seed=0x5EED0001):
     """G1ExpIONative records (x, offset, exp_val[8 x u32], output left zero -- filled from the chain
     result by `fill_g1_outputs`); exp_val is a full 256-bit value (reference g1/exp.rs:796)."""

@@ -79,6 +79,20 @@ def main():
                      "trace_cap0": ["%016x" % int.from_bytes(proof[4 + 8 * i:12 + 8 * i], "little") for i in range(4)]}
         print(name, out[name], flush=True)
         del trace, proof
+    # gadget test AIRs: G1Stark 512 rows (reference src/curves/g1/muladd.rs:463), Fq12Stark 512 rows (src/fields/fq12/mul.rs:364)
+    for name, air_id, n, gen in (("g1_muladd_512", orc.AIR_G1_MULADD, 512, syn.g1_muladd_ios), ("fq12_mul_512", orc.AIR_FQ12_MUL, 512, syn.fq12_mul_ios)):
+        if (only and name not in only) or ("--skip-new" in sys.argv):
+            if name in old:
+                out[name] = old[name]
+            continue
+        ios = gen(n)
+        air = orc.Air(air_id, n)
+        trace, _ = air.generate_trace(ios)
+        proof = air.prove(trace, np.zeros(0, dtype=np.uint64))
+        assert air.verify(proof)[0]
+        out[name] = {"ios_sha256": sha(ios), "trace_sha256": sha(trace.tobytes()), "proof_sha256": sha(proof), "proof_len": len(proof),
+                     "trace_cap0": ["%016x" % int.from_bytes(proof[4 + 8 * i:12 + 8 * i], "little") for i in range(4)]}
+        print(name, out[name], flush=True)
     json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 

@@ -320,3 +320,41 @@ def test_error_paths(ctx, sbn):
         g1.generate_trace(bytes(ios))
     # the context stays usable after errors
     assert sbn.prove(stark, stark.config(), tr, np.zeros(0, dtype=np.uint64)).to_bytes()
+
+
+@pytest.mark.parametrize("name,cls_name,air_attr,gen", [("g1_muladd_512", "G1Stark", "AIR_G1_MULADD", "g1_muladd_ios"), ("fq12_mul_512", "Fq12Stark", "AIR_FQ12_MUL", "fq12_mul_ios")])
+def test_gadget_airs_trace_and_proof_match_oracle(ctx, sbn, orc, golden, name, cls_name, air_attr, gen):
+    """G1Stark / Fq12Stark (the reference's gadget test AIRs, 512 rows as in the reference): columns and proof bytes equal the
+    oracle's; also at 4096 rows (split range check with N >> 256) against the oracle trace and the oracle verifier."""
+    n = 512
+    ios = getattr(sbn.synthetic, gen)(n)
+    stark = getattr(sbn, cls_name)(n, ctx)
+    trace = stark.generate_trace(ios)
+    cols = trace.download()
+    g = golden[name]
+    if hashlib.sha256(cols.tobytes()).hexdigest() != g["trace_sha256"]:
+        want, _ = orc.Air(getattr(orc, air_attr), n).generate_trace(ios)
+        pytest.fail("%s trace columns differ from the oracle: %s" % (cls_name, np.nonzero((cols != want).any(axis=1))[0][:20]))
+    pb = sbn.prove(stark, stark.config(), trace, np.zeros(0, dtype=np.uint64)).to_bytes()
+    assert len(pb) == g["proof_len"] and hashlib.sha256(pb).hexdigest() == g["proof_sha256"]
+    n = 4096
+    ios = getattr(sbn.synthetic, gen)(n, seed=77)
+    air = orc.Air(getattr(orc, air_attr), n)
+    stark = getattr(sbn, cls_name)(n, ctx)
+    trace = stark.generate_trace(ios)
+    want, _ = air.generate_trace(ios)
+    assert (trace.download() == want).all()
+    pb = sbn.prove(stark, stark.config(), trace, np.zeros(0, dtype=np.uint64)).to_bytes()
+    assert air.verify(pb) == (True, "")
+
+
+def test_gadget_air_input_errors(ctx, sbn):
+    ios = bytearray(sbn.synthetic.g1_muladd_ios(256))
+    ios[64:128] = ios[0:64]          # row 0: b = a, the addition gadget would divide by zero
+    with pytest.raises(sbn.SbnError, match="equal x"):
+        sbn.G1Stark(256, ctx).generate_trace(bytes(ios))
+    bad = bytearray(sbn.synthetic.fq12_mul_ios(256)); bad[0:32] = b"\xff" * 32
+    with pytest.raises(sbn.SbnError, match="canonical"):
+        sbn.Fq12Stark(256, ctx).generate_trace(bytes(bad))
+    with pytest.raises(sbn.SbnError, match="power of two"):
+        sbn.G1Stark(100, ctx)
