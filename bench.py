@@ -273,12 +273,15 @@ def main():
         ag = sharding.dist_allgather(device=torch.device("cuda", local))
         raw0 = gen_ios(NUM_IO, seed=0x5EED0001)          # the same inputs on every rank: the trace is replicated
 
+        sharded_phases = {}
+
         def step_sharded(single=False):
             tr = stark.generate_trace(raw0)
             ios = syn.fill_outputs(raw0, tr.results(), stark.io_size, out_off)
             pi = stark.generate_public_inputs(ios)
             p = sbn.prove(stark, cfg, tr, pi) if single else sbn.prove_sharded(stark, cfg, tr, pi, rank, world, ag)
             tr.free()
+            sharded_phases.update(p.timings)
             return p.to_bytes()
         for _ in range(2):
             sharded_bytes = step_sharded()
@@ -294,9 +297,10 @@ def main():
         import hashlib
         same = sharding.gather_digests({rank: sharded_bytes}, world, device="cuda")
         ok = len({d[0] for d in same}) == 1
+        phases_sh = {k: round(v, 3) for k, v in sharded_phases.items()}
         if rank == 0:
             ok = ok and hashlib.sha256(step_sharded(single=True)).hexdigest() == same[0][0]
-        intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok,
+        intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok, "phase_ms_rank0": phases_sh,
                  "collectives": "3 commitments x all_gather(cap digests) + all_gather(quotient values) + all_gather(opened rows), NCCL"}
 
     ms_total, e2e_ms = sharding.max_over_ranks([ms_total, e2e_s * 1000.0], device="cuda")

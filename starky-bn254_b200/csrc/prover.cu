@@ -324,15 +324,18 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   } else {
     // the rank that owns a leaf opens it: rows and paths live in its class batches, at the leaf's index inside the class
     const int logLp = logL - sh.m;
-    std::vector<u64> local_idx; std::vector<size_t> which;
-    for (size_t q = 0; q < nq; q++) if ((int)(indices[q] >> logLp) == sh.rank) { local_idx.push_back(indices[q] & ((u64(1) << logLp) - 1)); which.push_back(q); }
-    std::vector<u64> mine(rw_o * nq, 0), got(rw_o * local_idx.size());
-    if (!local_idx.empty()) fri_gather_queries(ctx, qo, logLp, 0, {}, local_idx, got.data());
-    for (size_t j = 0; j < which.size(); j++) memcpy(mine.data() + which[j] * rw_o, got.data() + j * rw_o, rw_o * 8);
+    std::vector<u64> local_idx;
+    for (size_t q = 0; q < nq; q++) if ((int)(indices[q] >> logLp) == sh.rank) local_idx.push_back(indices[q] & ((u64(1) << logLp) - 1));
+    // every rank knows all indices, hence how many queries each rank answers: blocks are padded to the largest count only
+    std::vector<size_t> count(sh.world, 0), slot(nq);
+    for (size_t q = 0; q < nq; q++) slot[q] = count[indices[q] >> logLp]++;
+    size_t max_count = 0; for (size_t c : count) max_count = std::max(max_count, c);
+    std::vector<u64> mine(rw_o * max_count, 0);
+    if (!local_idx.empty()) fri_gather_queries(ctx, qo, logLp, 0, {}, local_idx, mine.data());
     std::vector<uint8_t> all;
     sh.gather(mine.data(), mine.size() * 8, all);
     const u64* parts = reinterpret_cast<const u64*>(all.data());
-    for (size_t q = 0; q < nq; q++) memcpy(rec_o.data() + q * rw_o, parts + ((size_t)(indices[q] >> logLp) * nq + q) * rw_o, rw_o * 8);
+    for (size_t q = 0; q < nq; q++) memcpy(rec_o.data() + q * rw_o, parts + ((size_t)(indices[q] >> logLp) * max_count + slot[q]) * rw_o, rw_o * 8);
   }
   fri_gather_queries(ctx, {}, logn, rate_bits, lp, indices, rec_l.data());
   w.u32_((uint32_t)indices.size());
