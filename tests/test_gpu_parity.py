@@ -358,3 +358,26 @@ def test_gadget_air_input_errors(ctx, sbn):
         sbn.Fq12Stark(256, ctx).generate_trace(bytes(bad))
     with pytest.raises(sbn.SbnError, match="power of two"):
         sbn.G1Stark(100, ctx)
+
+
+def test_g1_256_instances_verifies(ctx, sbn, orc):
+    """BASELINE config 2 at 256 instances per proof (2^17 rows x 2 188 columns): a size the oracle prover is not run at;
+    the oracle's verifier must accept the GPU proof, and the chain results must equal big-integer group arithmetic."""
+    n = 256
+    syn = sbn.synthetic
+    ios = syn.g1_exp_ios(n, seed=99)
+    stark = sbn.G1ExpStark(n, ctx)
+    assert (stark.num_rows, stark.num_columns) == (1 << 17, 2188)
+    trace = stark.generate_trace(ios)
+    res = trace.results()
+    for i in (0, 200, 255):
+        b = ios[i * 224:(i + 1) * 224]
+        rd = lambda o: int.from_bytes(b[o:o + 32], "little")
+        want = syn.g1_add(syn.g1_mul((rd(0), rd(32)), rd(128)), (rd(64), rd(96)))
+        assert (int.from_bytes(res[i][:4].tobytes(), "little"), int.from_bytes(res[i][4:8].tobytes(), "little")) == want
+    full = syn.fill_g1_outputs(ios, res)
+    pb = sbn.prove(stark, stark.config(), trace, stark.generate_public_inputs(full)).to_bytes()
+    ok, why = orc.Air(orc.AIR_G1_EXP, n).verify(pb)
+    assert ok, why
+    t = bytearray(pb); t[len(t) // 2] ^= 2
+    assert not orc.Air(orc.AIR_G1_EXP, n).verify(bytes(t))[0]
