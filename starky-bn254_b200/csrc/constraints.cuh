@@ -17,10 +17,22 @@ struct F {
   HD F() : v(0) {}
   HD explicit F(u64 x) : v(x) {}
 };
+// On the device the value is an ARBITRARY 64-bit representative (lazy arithmetic of gl.cuh: no conditional subtraction of p
+// after each operation, four-multiplication products); it is canonicalised where it leaves the kernel (f_canon in quotient.cu).
+// On the host (tests/emu) the same code runs on canonical values.
+#ifdef __CUDA_ARCH__
+HD F operator+(F a, F b) { return F(gl_add_nc2(a.v, b.v)); }
+HD F operator-(F a, F b) { return F(gl_sub_nc2(a.v, b.v)); }
+HD F operator*(F a, F b) { return F(gl_mul_nc(a.v, b.v)); }
+HD F operator-(F a) { return F(gl_sub_nc2(0, a.v)); }
+HD u64 f_canon(F a) { return gl_canon(a.v); }
+#else
 HD F operator+(F a, F b) { return F(gl_add(a.v, b.v)); }
 HD F operator-(F a, F b) { return F(gl_sub(a.v, b.v)); }
 HD F operator*(F a, F b) { return F(gl_mul(a.v, b.v)); }
 HD F operator-(F a) { return F(gl_neg(a.v)); }
+HD u64 f_canon(F a) { return a.v; }
+#endif
 
 #define SBN_MAX_CHALLENGES 2
 

@@ -26,7 +26,7 @@ HD void qpoint_end(const QArgs& a, size_t idx, const QPoint& q) {
   for (int c = 0; c < SBN_MAX_CHALLENGES; c++) {
     u64* p = a.acc + (size_t)c * a.npoints + idx;
     F prev = a.first ? F() : F(*p) * F(a.alpha_m[c]);
-    *p = (prev + q.acc[c]).v;
+    *p = f_canon(prev + q.acc[c]);
   }
 }
 
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_fq12_products(QArgs a, int xa, int ya, 
   F acc[31];
   fq12_product_acc(q, xa, ya, oi, acc);
 #pragma unroll
-  for (int k = 0; k < 31; k++) prod[((size_t)oi * 31 + k) * N2 + idx] = acc[k].v;
+  for (int k = 0; k < 31; k++) prod[((size_t)oi * 31 + k) * N2 + idx] = f_canon(acc[k]);
 }
 
 template <int KIND> __global__ void __launch_bounds__(128) k_segment(QArgs a, Segment s) {
