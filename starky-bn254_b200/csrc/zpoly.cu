@@ -20,8 +20,8 @@ __device__ __forceinline__ void row_num_den(const u64* __restrict__ trace, size_
     u32 l = lhs[e];
     if (l == 0xFFFFFFFFu) break;
     u64 g = gamma[e];
-    num = gl_mul(num, gl_add(trace[(size_t)l * stride + r], g));
-    den = gl_mul(den, gl_add(trace[(size_t)rhs[e] * stride + r], g));
+    num = gl_mul_nc(num, gl_add_nc(trace[(size_t)l * stride + r], g));
+    den = gl_mul_nc(den, gl_add_nc(trace[(size_t)rhs[e] * stride + r], g));
   }
 }
 // block-wide inclusive multiplicative scans: prefix over v (result in pre) and suffix over w (result in suf).
@@ -33,8 +33,8 @@ __device__ __forceinline__ void block_scan_mul(u64 v, u64 w, u64& pre, u64& suf)
   u64 a = v, b = w;
   for (int d = 1; d < 32; d <<= 1) {
     u64 ta = __shfl_up_sync(0xffffffffu, a, d), tb = __shfl_down_sync(0xffffffffu, b, d);
-    if (lane >= d) a = gl_mul(a, ta);
-    if (lane + d < 32) b = gl_mul(b, tb);
+    if (lane >= d) a = gl_mul_nc(a, ta);
+    if (lane + d < 32) b = gl_mul_nc(b, tb);
   }
   if (lane == 31) sv[warp] = a;
   if (lane == 0) sw[warp] = b;
@@ -44,25 +44,25 @@ __device__ __forceinline__ void block_scan_mul(u64 v, u64 w, u64& pre, u64& suf)
     u64 px = x, sy = y;
     for (int d = 1; d < ZT / 32; d <<= 1) {
       u64 tx = __shfl_up_sync(0xffffffffu, px, d), ty = __shfl_down_sync(0xffffffffu, sy, d);
-      if (lane >= d) px = gl_mul(px, tx);
-      if (lane + d < ZT / 32) sy = gl_mul(sy, ty);
+      if (lane >= d) px = gl_mul_nc(px, tx);
+      if (lane + d < ZT / 32) sy = gl_mul_nc(sy, ty);
     }
     u64 ex = __shfl_up_sync(0xffffffffu, px, 1), ey = __shfl_down_sync(0xffffffffu, sy, 1);
     if (lane < ZT / 32) { sv[lane] = lane == 0 ? 1 : ex; sw[lane] = lane == ZT / 32 - 1 ? 1 : ey; }
   }
   __syncthreads();
-  pre = gl_mul(a, sv[warp]); suf = gl_mul(b, sw[warp]);
+  pre = gl_mul_nc(a, sv[warp]); suf = gl_mul_nc(b, sw[warp]);
   __syncthreads();
 }
 // block-wide products of v and of w (valid in thread 0)
 __device__ __forceinline__ void block_reduce_mul(u64 v, u64 w, u64& tv, u64& tw) {
   __shared__ u64 rv[ZT / 32], rw[ZT / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int d = 16; d >= 1; d >>= 1) { v = gl_mul(v, __shfl_xor_sync(0xffffffffu, v, d)); w = gl_mul(w, __shfl_xor_sync(0xffffffffu, w, d)); }
+  for (int d = 16; d >= 1; d >>= 1) { v = gl_mul_nc(v, __shfl_xor_sync(0xffffffffu, v, d)); w = gl_mul_nc(w, __shfl_xor_sync(0xffffffffu, w, d)); }
   if (lane == 0) { rv[warp] = v; rw[warp] = w; }
   __syncthreads();
   tv = 1; tw = 1;
-  if (threadIdx.x == 0) for (int i = 0; i < ZT / 32; i++) { tv = gl_mul(tv, rv[i]); tw = gl_mul(tw, rw[i]); }
+  if (threadIdx.x == 0) for (int i = 0; i < ZT / 32; i++) { tv = gl_mul_nc(tv, rv[i]); tw = gl_mul_nc(tw, rw[i]); }
 }
 
 __global__ void __launch_bounds__(ZT) k_z_tile_products(const u64* __restrict__ trace, size_t stride, const u32* lhs, const u32* rhs, const u64* gamma,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(ZT) k_z_tile_products(const u64* __restrict__ 
   row_num_den(trace, stride, r, lhs, rhs, gamma, batch, z, num, den);
   u64 tn, td;
   block_reduce_mul(num, den, tn, td);
-  if (threadIdx.x == 0) { tile_num[(size_t)z * ntiles + tile] = tn; tile_den[(size_t)z * ntiles + tile] = td; }
+  if (threadIdx.x == 0) { tile_num[(size_t)z * ntiles + tile] = gl_canon(tn); tile_den[(size_t)z * ntiles + tile] = gl_canon(td); }
 }
 // per column: tile_num -> exclusive prefix, tile_den -> exclusive suffix times 1/prod(all den)
 __global__ void k_z_tile_scan(u64* tile_num, u64* tile_den, int ntiles, int nz) {
@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(ZT) k_z_finish(const u64* __restrict__ trace, 
   if ((threadIdx.x & 31) == 31) warp_last[threadIdx.x >> 5] = pre;
   __syncthreads();
   if ((threadIdx.x & 31) == 0) pre_ex = threadIdx.x == 0 ? 1 : warp_last[(threadIdx.x >> 5) - 1];
-  u64 v = gl_mul(gl_mul(pre_ex, tile_num[(size_t)z * ntiles + tile]), gl_mul(suf, tile_den[(size_t)z * ntiles + tile]));
-  zout[(size_t)z * N + r] = v;
+  u64 v = gl_mul_nc(gl_mul_nc(pre_ex, tile_num[(size_t)z * ntiles + tile]), gl_mul_nc(suf, tile_den[(size_t)z * ntiles + tile]));
+  zout[(size_t)z * N + r] = gl_canon(v);   // products ran on lazy representatives (gl.cuh)
 }
 
 void compute_z_polys(sbn_ctx* ctx, const u64* trace, int logn, const PermInstances& perm, u64* z_out) {
