@@ -271,6 +271,7 @@ def main():
     intra = None
     if world > 1 and world in (2, 4, 8, 16) and not args.no_intra_proof:
         ag = sharding.dist_allgather(device=torch.device("cuda", local))
+        agd = sharding.dist_allgather_device(torch.device("cuda", local))
         raw0 = gen_ios(NUM_IO, seed=0x5EED0001)          # the same inputs on every rank: the trace is replicated
 
         sharded_phases = {}
@@ -279,7 +280,7 @@ def main():
             tr = stark.generate_trace(raw0)
             ios = syn.fill_outputs(raw0, tr.results(), stark.io_size, out_off)
             pi = stark.generate_public_inputs(ios)
-            p = sbn.prove(stark, cfg, tr, pi) if single else sbn.prove_sharded(stark, cfg, tr, pi, rank, world, ag)
+            p = sbn.prove(stark, cfg, tr, pi) if single else sbn.prove_sharded(stark, cfg, tr, pi, rank, world, ag, allgather_device=agd)
             tr.free()
             sharded_phases.update(p.timings)
             return p.to_bytes()

@@ -114,7 +114,10 @@ int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, co
  * with the same sizes on every rank: once per commitment (cap digests), once for the quotient values, once for the opened rows.
  * Needs rate_bits = 1 and world <= 2^cap_height.  world = 1 is sbn_prove. */
 typedef int (*sbn_allgather_fn)(void* user, const void* send, size_t nbytes, void* recv);
-typedef struct { uint32_t rank, world; sbn_allgather_fn allgather; void* user; } sbn_shard;
+/* `allgather_device` (optional, may be NULL): the same exchange on DEVICE buffers of this rank's GPU (ncclAllGather), used for
+ * the quotient values so that they never pass through the host; the library has synchronised its stream before the call and
+ * the callback must return only when `recv` is complete.  NULL: the values are staged through host memory and `allgather`. */
+typedef struct { uint32_t rank, world; sbn_allgather_fn allgather; void* user; sbn_allgather_fn allgather_device; } sbn_shard;
 int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,
                       const sbn_shard* shard, sbn_proof** out);
 /* Canonical little-endian wire format (DESIGN.md "Proof wire format").  Call with buf == NULL to get the length. */

@@ -50,7 +50,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 
 class Shard(C.Structure):
     """sbn_shard (include/starky_bn254_b200.h): this rank's place in an intra-proof sharding group."""
-    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", C.c_void_p)]
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", C.c_void_p), ("allgather_device", ALLGATHER_FN)]
 
 
 def lib():
@@ -340,10 +340,12 @@ def prove(stark, config, trace, public_inputs, timing=None):
     return proof
 
 
-def prove_sharded(stark, config, trace, public_inputs, rank, world, allgather, timing=None):
+def prove_sharded(stark, config, trace, public_inputs, rank, world, allgather, timing=None, allgather_device=None):
     """One proof computed by `world` (2, 4, 8, 16) cooperating ranks, one GPU each: `sbn_prove_sharded`.  Every rank passes the
     same (replicated) trace and public inputs and gets the full proof, byte-identical to `prove`'s.  `allgather(data: bytes)`
-    returns the list of every rank's `data` in rank order (see sharding.dist_allgather / sharding.ThreadGroup)."""
+    returns the list of every rank's `data` in rank order (see sharding.dist_allgather / sharding.ThreadGroup).
+    `allgather_device(send_ptr, nbytes, recv_ptr)` (optional) does the same between device buffers (sharding.dist_allgather_device):
+    the quotient values then never pass through the host."""
     ctx = trace.ctx
     pi = np.ascontiguousarray(public_inputs, dtype=np.uint64)
     failure = []
@@ -359,7 +361,15 @@ def prove_sharded(stark, config, trace, public_inputs, rank, world, allgather, t
             failure.append(e)
             return 1
 
-    shard = Shard(rank, world, ALLGATHER_FN(cb), None)
+    def cb_dev(user, send, nbytes, recv):
+        try:
+            allgather_device(send, nbytes, recv)
+            return 0
+        except BaseException as e:
+            failure.append(e)
+            return 1
+
+    shard = Shard(rank, world, ALLGATHER_FN(cb), None, ALLGATHER_FN(cb_dev) if allgather_device is not None else ALLGATHER_FN())
     h = C.c_void_p()
     rc = lib().sbn_prove_sharded(ctx.h, C.byref(config), trace.h, _ptr(pi), len(pi), C.byref(shard), C.byref(h))
     if failure:

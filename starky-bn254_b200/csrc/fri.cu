@@ -6,11 +6,17 @@
 #include "ntt.cuh"
 #include "poseidon.cuh"
 
+// out[i] = base^i (extension field, SoA): a thread raises base to the first exponent of its run of 16 and multiplies from there
+#define EXTPOW_RUN 16
 __global__ void k_ext_powers(u64* out_a, u64* out_b, gl2 base, size_t n) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  gl2 r = gl2_pow(base, i);
-  out_a[i] = r.a; out_b[i] = r.b;
+  const size_t i0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * EXTPOW_RUN;
+  if (i0 >= n) return;
+  gl2 r = gl2_pow(base, i0);
+  for (size_t i = i0; i < n && i < i0 + EXTPOW_RUN; i++) { out_a[i] = r.a; out_b[i] = r.b; r = gl2_mul(r, base); }
+}
+static void launch_ext_powers(sbn_ctx* ctx, u64* out_a, u64* out_b, gl2 base, size_t n) {
+  const size_t threads = (n + EXTPOW_RUN - 1) / EXTPOW_RUN;
+  k_ext_powers<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(out_a, out_b, base, n); LAUNCH_CHECK(ctx);
 }
 
 // ---- openings ----
@@ -34,21 +40,24 @@ __global__ void __launch_bounds__(256) k_eval_two_points(const u64* __restrict__
   if (threadIdx.x < 4) out[(size_t)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
 }
 
-static DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1) {
+DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1) {
   size_t N = size_t(1) << logn;
   DevBuf<u64> pw(ctx, 4 * N);
-  unsigned bl = (unsigned)((N + 255) / 256);
-  k_ext_powers<<<bl, 256, 0, ctx->stream>>>(pw, pw + N, z0, N); LAUNCH_CHECK(ctx);
-  k_ext_powers<<<bl, 256, 0, ctx->stream>>>(pw + 2 * N, pw + 3 * N, z1, N); LAUNCH_CHECK(ctx);
+  launch_ext_powers(ctx, pw, pw + N, z0, N);
+  launch_ext_powers(ctx, pw + 2 * N, pw + 3 * N, z1, N);
   return pw;
 }
 
-void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, gl2 zeta, gl2 zeta_next, u64* d_out) {
+void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, const u64* pw, u64* d_out) {
   if (ncols <= 0) return;
-  DevBuf<u64> pw = two_point_power_table(ctx, logn, zeta, zeta_next);
   KScope ks(ctx, "openings_eval");
   k_eval_two_points<<<ncols, 256, 0, ctx->stream>>>(coeffs, size_t(1) << logn, pw, d_out);
   LAUNCH_CHECK(ctx);
+}
+void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, gl2 zeta, gl2 zeta_next, u64* d_out) {
+  if (ncols <= 0) return;
+  DevBuf<u64> pw = two_point_power_table(ctx, logn, zeta, zeta_next);
+  eval_columns_at_two_points(ctx, coeffs, ncols, logn, pw, d_out);
 }
 
 // ---- batch reduction: partial[g][2][N] = sum over the g-th slice of columns of alpha^j f_j ----
@@ -74,27 +83,63 @@ __global__ void k_sum_partials(const u64* partial, int ngroups, size_t N, u64* o
   out[i] = s;
 }
 
+// out[i] = base[i] + sum_{r < nparts} parts[r * stride + offset + i], i < n
+__global__ void k_sum_strided(const u64* __restrict__ parts, int nparts, size_t stride, size_t offset, size_t n, u64* __restrict__ out, const u64* __restrict__ base) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 s = base ? base[i] : 0;
+  for (int r = 0; r < nparts; r++) s = gl_add(s, parts[(size_t)r * stride + offset + i]);
+  out[i] = s;
+}
+
 // ---- (comp(X) - comp(z)) / (X - z):  Q[i] = z^-(i+1) * sum_{j>i} comp[j] z^j, Q[N-1] = 0 ----
-// Single block; thread t owns a contiguous chunk.  comp [2][N]; zp = z^j, zi = z^-j (ext SoA tables).
-__global__ void __launch_bounds__(1024) k_divide_by_linear(const u64* __restrict__ comp, size_t N, const u64* __restrict__ zp, const u64* __restrict__ zi,
-                                                           u64* __restrict__ q /* [2][N] */) {
-  __shared__ u64 tot_a[1024], tot_b[1024];
-  size_t chunk = (N + blockDim.x - 1) / blockDim.x;
-  size_t lo = (size_t)threadIdx.x * chunk, hi = min(N, lo + chunk);
+// A suffix sum in three steps: every thread sums its run of DIV_RUN terms, one block turns the run totals into exclusive suffix
+// sums, every thread walks its run from the top.  comp [2][N]; zp = z^j, zi = z^-j (ext SoA tables, stride N).
+#define DIV_RUN 16
+__global__ void __launch_bounds__(256) k_div_run_sums(const u64* __restrict__ comp, size_t N, const u64* __restrict__ zp, u64* __restrict__ tot /* [2][T] */, size_t T) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const size_t lo = t * DIV_RUN, hi = min(N, lo + DIV_RUN);
   gl2 s = gl2_make(0, 0);
   for (size_t j = lo; j < hi; j++) s = gl2_add(s, gl2_mul(gl2_make(comp[j], comp[N + j]), gl2_make(zp[j], zp[N + j])));
-  tot_a[threadIdx.x] = s.a; tot_b[threadIdx.x] = s.b;
+  tot[t] = s.a; tot[T + t] = s.b;
+}
+__global__ void __launch_bounds__(1024) k_div_suffix(u64* __restrict__ tot /* [2][T]: totals in, exclusive suffix sums out */, size_t T) {
+  __shared__ u64 pa[1024], pb[1024];
+  const size_t chunk = (T + blockDim.x - 1) / blockDim.x;
+  const size_t lo = min(T, (size_t)threadIdx.x * chunk), hi = min(T, lo + chunk);
+  gl2 s = gl2_make(0, 0);
+  for (size_t j = lo; j < hi; j++) s = gl2_add(s, gl2_make(tot[j], tot[T + j]));
+  pa[threadIdx.x] = s.a; pb[threadIdx.x] = s.b;
   __syncthreads();
-  gl2 suffix = gl2_make(0, 0);  // sum over chunks after mine
-  for (int t = threadIdx.x + 1; t < (int)blockDim.x; t++) suffix = gl2_add(suffix, gl2_make(tot_a[t], tot_b[t]));
-  // walk my chunk from the top: running = sum_{j > i} comp[j] z^j
-  gl2 running = suffix;
+  gl2 running = gl2_make(0, 0);   // sum over the pieces after mine
+  for (int u = threadIdx.x + 1; u < (int)blockDim.x; u++) running = gl2_add(running, gl2_make(pa[u], pb[u]));
+  for (size_t j = hi; j-- > lo;) {
+    const gl2 v = gl2_make(tot[j], tot[T + j]);
+    tot[j] = running.a; tot[T + j] = running.b;
+    running = gl2_add(running, v);
+  }
+}
+__global__ void __launch_bounds__(256) k_div_finish(const u64* __restrict__ comp, size_t N, const u64* __restrict__ zp, const u64* __restrict__ zi,
+                                                    const u64* __restrict__ suf /* [2][T] */, size_t T, u64* __restrict__ q /* [2][N] */) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const size_t lo = t * DIV_RUN, hi = min(N, lo + DIV_RUN);
+  gl2 running = gl2_make(suf[t], suf[T + t]);   // sum_{j >= hi} comp[j] z^j
   for (size_t i = hi; i-- > lo;) {
     gl2 v;
     if (i + 1 < N) v = gl2_mul(running, gl2_make(zi[i + 1], zi[N + i + 1])); else v = gl2_make(0, 0);
     q[i] = v.a; q[N + i] = v.b;
     running = gl2_add(running, gl2_mul(gl2_make(comp[i], comp[N + i]), gl2_make(zp[i], zp[N + i])));
   }
+}
+static void divide_by_linear(sbn_ctx* ctx, const u64* comp, size_t N, const u64* zp, const u64* zi, u64* q) {
+  const size_t T = (N + DIV_RUN - 1) / DIV_RUN;
+  DevBuf<u64> tot(ctx, 2 * T);
+  KScope ks(ctx, "fri_divide_by_linear");
+  k_div_run_sums<<<(unsigned)((T + 255) / 256), 256, 0, ctx->stream>>>(comp, N, zp, tot, T); LAUNCH_CHECK(ctx);
+  k_div_suffix<<<1, 1024, 0, ctx->stream>>>(tot, T); LAUNCH_CHECK(ctx);
+  k_div_finish<<<(unsigned)((T + 255) / 256), 256, 0, ctx->stream>>>(comp, N, zp, zi, tot, T, q); LAUNCH_CHECK(ctx);
 }
 // final = q0 * shift + q1, written into the first N entries of the zero-padded [2][L] coefficient array
 __global__ void k_combine_final(const u64* q0, const u64* q1, gl2 shift, size_t N, size_t L, u64* out) {
@@ -106,34 +151,49 @@ __global__ void k_combine_final(const u64* q0, const u64* q1, gl2 shift, size_t 
 }
 
 void fri_final_poly(sbn_ctx* ctx, const std::vector<OracleView>& oracles, int logn, int rate_bits, gl2 alpha, gl2 zeta, gl2 zeta_next,
-                    u64* d_final_coeffs) {
+                    u64* d_final_coeffs, const ColumnSplit* split, const u64* pw) {
   const size_t N = size_t(1) << logn, L = N << rate_bits;
   int total = 0; for (auto& o : oracles) total += o.ncols;
   int n1 = total - oracles.back().ncols;   // the zeta_next batch omits the last oracle (quotient polys)
   // alpha^j table (ext SoA)
   DevBuf<u64> apow(ctx, 2 * (size_t)total);
-  k_ext_powers<<<(total + 255) / 256, 256, 0, ctx->stream>>>(apow, apow + total, alpha, total); LAUNCH_CHECK(ctx);
+  launch_ext_powers(ctx, apow, apow + total, alpha, total);
   const int G = 16;
-  DevBuf<u64> partial(ctx, (size_t)G * 2 * N), comp1(ctx, 2 * N), comp0(ctx, 2 * N);
+  const int world = split ? split->world : 1, rank = split ? split->rank : 0;
+  // mine[0] = my share of the oracles both batches contain, mine[1] = my share of the last oracle (zeta batch only)
+  DevBuf<u64> partial(ctx, (size_t)G * 2 * N), mine(ctx, 4 * N), comp1(ctx, 2 * N), comp0(ctx, 2 * N);
+  CUDA_CHECK(cudaMemsetAsync(mine, 0, 4 * N * 8, ctx->stream));
   int off = 0;
   for (size_t o = 0; o < oracles.size(); o++) {
-    int nc = oracles[o].ncols;
-    int cpg = (nc + G - 1) / G, ng = (nc + cpg - 1) / cpg;
-    dim3 grid((unsigned)((N + 255) / 256), ng);
-    KScope ks(ctx, "fri_reduce_columns");
-    k_reduce_columns<<<grid, 256, 0, ctx->stream>>>(oracles[o].coeffs, N, nc, cpg, apow, apow + total, off, partial); LAUNCH_CHECK(ctx);
-    bool last = o + 1 == oracles.size();
-    if (last) CUDA_CHECK(cudaMemcpyAsync(comp0, comp1, 2 * N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_sum_partials<<<(unsigned)((2 * N + 255) / 256), 256, 0, ctx->stream>>>(partial, ng, N, last ? comp0 : comp1, (o > 0) ? 1 : 0); LAUNCH_CHECK(ctx);
-    off += nc;
+    const int nc_all = oracles[o].ncols, per = (nc_all + world - 1) / world;
+    const int c0 = std::min(nc_all, rank * per), nc = std::min(nc_all, c0 + per) - c0;
+    const bool last = o + 1 == oracles.size();
+    if (nc > 0) {
+      int cpg = (nc + G - 1) / G, ng = (nc + cpg - 1) / cpg;
+      dim3 grid((unsigned)((N + 255) / 256), ng);
+      KScope ks(ctx, "fri_reduce_columns");
+      k_reduce_columns<<<grid, 256, 0, ctx->stream>>>(oracles[o].coeffs + (size_t)c0 * N, N, nc, cpg, apow, apow + total, off + c0, partial); LAUNCH_CHECK(ctx);
+      k_sum_partials<<<(unsigned)((2 * N + 255) / 256), 256, 0, ctx->stream>>>(partial, ng, N, mine + (last ? 2 * N : 0), 1); LAUNCH_CHECK(ctx);
+    }
+    off += nc_all;
   }
-  // quotients of the two batches
-  DevBuf<u64> q0(ctx, 2 * N), q1(ctx, 2 * N);
-  for (int b = 0; b < 2; b++) {
-    gl2 z = b == 0 ? zeta : zeta_next;
-    DevBuf<u64> pw = two_point_power_table(ctx, logn, z, gl2_inv(z));
-    k_divide_by_linear<<<1, 1024, 0, ctx->stream>>>(b == 0 ? comp0 : comp1, N, pw, pw + 2 * N, b == 0 ? q0 : q1); LAUNCH_CHECK(ctx);
+  if (world > 1) {
+    DevBuf<u64> all(ctx, (size_t)world * 4 * N);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    split->gather_device(mine, 4 * N * 8, all);
+    // comp1 = sum_r all[r][0], comp0 = comp1 + sum_r all[r][1]: the blocks are laid out as `2 world` partials of [2][N]
+    k_sum_strided<<<(unsigned)((2 * N + 255) / 256), 256, 0, ctx->stream>>>(all, world, 4 * N, 0, 2 * N, comp1, nullptr); LAUNCH_CHECK(ctx);
+    k_sum_strided<<<(unsigned)((2 * N + 255) / 256), 256, 0, ctx->stream>>>(all, world, 4 * N, 2 * N, 2 * N, comp0, comp1); LAUNCH_CHECK(ctx);
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(comp1, mine, 2 * N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_sum_strided<<<(unsigned)((2 * N + 255) / 256), 256, 0, ctx->stream>>>(mine, 1, 4 * N, 2 * N, 2 * N, comp0, comp1); LAUNCH_CHECK(ctx);
   }
+  // quotients of the two batches: z^j from the caller's table when it has one, z^-j built here
+  DevBuf<u64> q0(ctx, 2 * N), q1(ctx, 2 * N), own_pw;
+  if (!pw) { own_pw = two_point_power_table(ctx, logn, zeta, zeta_next); pw = own_pw; }
+  DevBuf<u64> pwi = two_point_power_table(ctx, logn, gl2_inv(zeta), gl2_inv(zeta_next));
+  divide_by_linear(ctx, comp0, N, pw, pwi, q0);
+  divide_by_linear(ctx, comp1, N, pw + 2 * N, pwi + 2 * N, q1);
   gl2 shift = gl2_pow(alpha, (u64)n1);
   k_combine_final<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(q0, q1, shift, N, L, d_final_coeffs); LAUNCH_CHECK(ctx);
 }

@@ -64,13 +64,17 @@ struct sbn_proof {
 // FRI layers, transcript) is replicated and deterministic, so the only exchanges are all-gathers of cap digests, of the
 // quotient values (2 N num_challenges field elements in total) and of the opened rows with their paths.
 struct Shard {
-  int rank = 0, world = 1, m = 0; sbn_allgather_fn allgather = nullptr; void* user = nullptr;
+  int rank = 0, world = 1, m = 0; sbn_allgather_fn allgather = nullptr; void* user = nullptr; sbn_allgather_fn allgather_device = nullptr;
   bool on() const { return world > 1; }
   u32 rho() const { return bitrev32((u32)rank, m); }
   void gather(const void* send, size_t nbytes, std::vector<uint8_t>& recv) const {
     recv.resize(nbytes * world);
     int rc = allgather(user, send, nbytes, recv.data());
     if (rc != 0) throw SbnError(SBN_ERR_INTERNAL, "sharded prove: the all-gather callback failed");
+  }
+  void gather_device(sbn_ctx* ctx, const void* d_send, size_t nbytes, void* d_recv) const {   // device buffers, stream-ordered on both sides
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (allgather_device(user, d_send, nbytes, d_recv) != 0) throw SbnError(SBN_ERR_INTERNAL, "sharded prove: the device all-gather callback failed");
   }
 };
 
@@ -128,6 +132,19 @@ static std::vector<int> reduction_arity_bits(const sbn_config& c, int degree_bit
     r.push_back(c.fri_arity_bits); degree_bits -= c.fri_arity_bits;
   }
   return r;
+}
+
+// quotient values of all classes, parts[rank][challenge][t] at quotient-coset index iq = bitrev_m(rank) + (t << m), into the
+// unsharded layout full[challenge][iq & 1][iq >> 1]
+__global__ void k_scatter_classes(const u64* __restrict__ parts, u64* __restrict__ full, int m, int nch, int logn) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int logMp = logn + 1 - m;
+  const size_t Mp = size_t(1) << logMp, N = size_t(1) << logn;
+  if (i >= ((size_t)nch << (logn + 1))) return;
+  const size_t t = i & (Mp - 1), rc = i >> logMp;
+  const int c = (int)(rc % nch), r = (int)(rc / nch);
+  const size_t iq = bitrev32((u32)r, m) + (t << m);
+  full[(size_t)c * 2 * N + (iq & 1) * N + (iq >> 1)] = parts[i];
 }
 
 static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr, const u64* public_inputs, size_t npis, const Shard& sh, sbn_proof* proof) {
@@ -213,22 +230,30 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     const size_t Mp = quotient_points(dom, logn);
     DevBuf<u64> acc_local(ctx, (size_t)SBN_MAX_CHALLENGES * Mp), acc_full(ctx, (size_t)nch * 2 * N);
     quotient_eval(ctx, air, dom, nullptr, nullptr, perm, d_pis, alphas, nch, logn, rate_bits, acc_local);
-    std::vector<u64> mine((size_t)nch * Mp), full((size_t)nch * 2 * N);
-    CUDA_CHECK(cudaMemcpyAsync(mine.data(), acc_local, mine.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    std::vector<uint8_t> all;
-    sh.gather(mine.data(), mine.size() * 8, all);
-    const u64* parts = reinterpret_cast<const u64*>(all.data());
-    for (int r = 0; r < sh.world; r++) {
-      const size_t sigma = bitrev32((u32)r, sh.m);
-      for (int c = 0; c < nch; c++) {
-        const u64* src = parts + ((size_t)r * nch + c) * Mp;
-        u64* dst = full.data() + (size_t)c * 2 * N;
-        for (size_t t = 0; t < Mp; t++) { const size_t iq = sigma + ((size_t)t << sh.m); dst[(iq & 1) * N + (iq >> 1)] = src[t]; }
+    if (sh.allgather_device) {   // device to device over NVLink, then one scatter kernel
+      DevBuf<u64> parts(ctx, (size_t)sh.world * nch * Mp);
+      sh.gather_device(ctx, acc_local, (size_t)nch * Mp * 8, parts);
+      const size_t tot = (size_t)sh.world * nch * Mp;
+      k_scatter_classes<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(parts, acc_full, sh.m, nch, logn);
+      LAUNCH_CHECK(ctx);
+    } else {
+      std::vector<u64> mine((size_t)nch * Mp), full((size_t)nch * 2 * N);
+      CUDA_CHECK(cudaMemcpyAsync(mine.data(), acc_local, mine.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      std::vector<uint8_t> all;
+      sh.gather(mine.data(), mine.size() * 8, all);
+      const u64* parts = reinterpret_cast<const u64*>(all.data());
+      for (int r = 0; r < sh.world; r++) {
+        const size_t sigma = bitrev32((u32)r, sh.m);
+        for (int c = 0; c < nch; c++) {
+          const u64* src = parts + ((size_t)r * nch + c) * Mp;
+          u64* dst = full.data() + (size_t)c * 2 * N;
+          for (size_t t = 0; t < Mp; t++) { const size_t iq = sigma + ((size_t)t << sh.m); dst[(iq & 1) * N + (iq >> 1)] = src[t]; }
+        }
       }
+      CUDA_CHECK(cudaMemcpyAsync(acc_full, full.data(), full.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
-    CUDA_CHECK(cudaMemcpyAsync(acc_full, full.data(), full.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     quotient_finish(ctx, acc_full, nch, logn, q_c.coeffs);
   }
   tm.mark("compute quotient polys");
@@ -248,13 +273,36 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   if (gl2_eq(gl2_pow(zeta, (u64)N), gl2_make(1, 0))) throw SbnError(SBN_ERR_INTERNAL, "Opening point is in the subgroup.");
   gl2 zeta_next = gl2_mul_base(zeta, g);
   const int C = (int)air.num_columns, Z = uses_perm ? z_c.ncols : 0;
-  DevBuf<u64> d_open(ctx, (size_t)(C + Z + nq_polys) * 4);
-  eval_columns_at_two_points(ctx, trace_c.coeffs, C, logn, zeta, zeta_next, d_open);
-  if (Z) eval_columns_at_two_points(ctx, z_c.coeffs, Z, logn, zeta, zeta_next, d_open + (size_t)C * 4);
-  eval_columns_at_two_points(ctx, q_c.coeffs, nq_polys, logn, zeta, zeta_next, d_open + (size_t)(C + Z) * 4);
   std::vector<u64> open((size_t)(C + Z + nq_polys) * 4);
-  CUDA_CHECK(cudaMemcpyAsync(open.data(), d_open, open.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  DevBuf<u64> zpw = two_point_power_table(ctx, logn, zeta, zeta_next);   // zeta^j, (g zeta)^j: shared by the openings and the FRI quotients
+  if (!sh.on()) {
+    DevBuf<u64> d_open(ctx, (size_t)(C + Z + nq_polys) * 4);
+    eval_columns_at_two_points(ctx, trace_c.coeffs, C, logn, zpw, d_open);
+    if (Z) eval_columns_at_two_points(ctx, z_c.coeffs, Z, logn, zpw, d_open + (size_t)C * 4);
+    eval_columns_at_two_points(ctx, q_c.coeffs, nq_polys, logn, zpw, d_open + (size_t)(C + Z) * 4);
+    CUDA_CHECK(cudaMemcpyAsync(open.data(), d_open, open.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  } else {
+    // every rank evaluates its slice of the columns of each commitment; the values (4 words per column) are all-gathered
+    const u64* cf[3] = {trace_c.coeffs.get(), Z ? z_c.coeffs.get() : nullptr, q_c.coeffs.get()};
+    const int ncs[3] = {C, Z, nq_polys};
+    int per[3], tot_per = 0;
+    for (int o = 0; o < 3; o++) { per[o] = (ncs[o] + sh.world - 1) / sh.world; tot_per += per[o]; }
+    DevBuf<u64> d_mine(ctx, (size_t)tot_per * 4);
+    CUDA_CHECK(cudaMemsetAsync(d_mine, 0, (size_t)tot_per * 32, ctx->stream));
+    for (int o = 0, at = 0; o < 3; at += per[o], o++) {
+      const int c0 = std::min(ncs[o], sh.rank * per[o]), nc = std::min(ncs[o], c0 + per[o]) - c0;
+      if (nc > 0) eval_columns_at_two_points(ctx, cf[o] + (size_t)c0 * N, nc, logn, zpw, d_mine + (size_t)at * 4);
+    }
+    std::vector<u64> mine((size_t)tot_per * 4);
+    CUDA_CHECK(cudaMemcpyAsync(mine.data(), d_mine, mine.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint8_t> all;
+    sh.gather(mine.data(), mine.size() * 8, all);
+    const u64* parts = reinterpret_cast<const u64*>(all.data());
+    for (int o = 0, at = 0, first = 0; o < 3; at += per[o], first += ncs[o], o++)
+      for (int c = 0; c < ncs[o]; c++) memcpy(open.data() + (size_t)(first + c) * 4, parts + ((size_t)(c / per[o]) * tot_per + at + c % per[o]) * 4, 32);
+  }
   // StarkOpeningSet { local_values, next_values, permutation_zs, permutation_zs_next, quotient_polys }
   auto pick = [&](int first, int count, int which) { std::vector<u64> v((size_t)count * 2); for (int i = 0; i < count; i++) { v[2 * i] = open[(size_t)(first + i) * 4 + 2 * which]; v[2 * i + 1] = open[(size_t)(first + i) * 4 + 2 * which + 1]; } return v; };
   std::vector<u64> local_values = pick(0, C, 0), next_values = pick(0, C, 1), pzs = pick(C, Z, 0), pzs_next = pick(C, Z, 1), qp = pick(C + Z, nq_polys, 0);
@@ -271,7 +319,8 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   std::vector<OracleView> views; views.push_back({trace_c.coeffs, C}); if (Z) views.push_back({z_c.coeffs, Z}); views.push_back({q_c.coeffs, nq_polys});
   const int logL = logn + rate_bits;
   DevBuf<u64> fcoeffs(ctx, 2 * L), fvalues(ctx, 2 * L);
-  fri_final_poly(ctx, views, logn, rate_bits, fri_alpha, zeta, zeta_next, fcoeffs);
+  ColumnSplit split{sh.rank, sh.world, [&](const void* a, size_t n, void* b) { sh.gather_device(ctx, a, n, b); }};
+  fri_final_poly(ctx, views, logn, rate_bits, fri_alpha, zeta, zeta_next, fcoeffs, sh.on() && sh.allgather_device ? &split : nullptr, zpw);
   tm.mark("reduce batch of polynomials");
   u64 shift = GL_MULT_GENERATOR;
   ntt_batch(ctx, fcoeffs, L, fvalues, L, 2, logL, false, shift, nullptr);
@@ -507,7 +556,7 @@ int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* t
   SBN_REQUIRE(trace->ctx == ctx, "trace belongs to another context");
   SBN_REQUIRE(shard->world >= 1 && shard->world <= 16 && (shard->world & (shard->world - 1)) == 0 && shard->rank < shard->world, "bad shard description");
   CUDA_CHECK(cudaSetDevice(ctx->device));
-  Shard sh; sh.rank = (int)shard->rank; sh.world = (int)shard->world; sh.allgather = shard->allgather; sh.user = shard->user;
+  Shard sh; sh.rank = (int)shard->rank; sh.world = (int)shard->world; sh.allgather = shard->allgather; sh.user = shard->user; sh.allgather_device = shard->allgather_device;
   while ((1 << sh.m) < sh.world) sh.m++;
   std::unique_ptr<sbn_proof> p(new sbn_proof());
   prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, sh, p.get());

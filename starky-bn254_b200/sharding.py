@@ -63,6 +63,27 @@ def dist_allgather(group=None, device=None):
     return allgather
 
 
+class _DevView:
+    """A raw device pointer as a 1-D uint8 array for torch.as_tensor (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def dist_allgather_device(device, group=None):
+    """Device-to-device all-gather for `prove_sharded(..., allgather_device=...)`: NCCL all_gather_into_tensor directly on the
+    library's buffers (viewed through __cuda_array_interface__), no host staging."""
+    world = dist.get_world_size(group)
+
+    def allgather(send_ptr, nbytes, recv_ptr):
+        s = torch.as_tensor(_DevView(send_ptr, nbytes), device=device)
+        r = torch.as_tensor(_DevView(recv_ptr, nbytes * world), device=device)
+        dist.all_gather_into_tensor(r, s, group=group)
+        torch.cuda.current_stream(device).synchronize()
+
+    return allgather
+
+
 class ThreadGroup:
     """In-process exchange for `world` ranks running as threads (one sbn context each, same or different GPUs)."""
 
