@@ -270,39 +270,42 @@ def main():
     # quotient values, opened rows) are NCCL all-gathers.  Reported beside the throughput number, not instead of it. ----
     intra = None
     if world > 1 and world in (2, 4, 8, 16) and not args.no_intra_proof:
-        ag = sharding.dist_allgather(device=torch.device("cuda", local))
-        agd = sharding.dist_allgather_device(torch.device("cuda", local))
-        raw0 = gen_ios(NUM_IO, seed=0x5EED0001)          # the same inputs on every rank: the trace is replicated
+        try:   # the headline numbers above must survive a failure of this extra measurement
+            ag = sharding.dist_allgather(device=torch.device("cuda", local))
+            agd = sharding.dist_allgather_device(torch.device("cuda", local))
+            raw0 = gen_ios(NUM_IO, seed=0x5EED0001)          # the same inputs on every rank: the trace is replicated
 
-        sharded_phases = {}
+            sharded_phases = {}
 
-        def step_sharded(single=False):
-            tr = stark.generate_trace(raw0)
-            ios = syn.fill_outputs(raw0, tr.results(), stark.io_size, out_off)
-            pi = stark.generate_public_inputs(ios)
-            p = sbn.prove(stark, cfg, tr, pi) if single else sbn.prove_sharded(stark, cfg, tr, pi, rank, world, ag, allgather_device=agd)
-            tr.free()
-            sharded_phases.update(p.timings)
-            return p.to_bytes()
-        for _ in range(2):
-            sharded_bytes = step_sharded()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        nsh = 4
-        for _ in range(nsh):
-            sharded_bytes = step_sharded()
-        s1.record(stream)
-        barrier()
-        sh_ms = sharding.max_over_ranks([s0.elapsed_time(s1) / nsh], device="cuda")[0]
-        import hashlib
-        same = sharding.gather_digests({rank: sharded_bytes}, world, device="cuda")
-        ok = len({d[0] for d in same}) == 1
-        phases_sh = {k: round(v, 3) for k, v in sharded_phases.items()}
-        if rank == 0:
-            ok = ok and hashlib.sha256(step_sharded(single=True)).hexdigest() == same[0][0]
-        intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok, "phase_ms_rank0": phases_sh,
-                 "collectives": "3 commitments x all_gather(cap digests) + all_gather(quotient values) + all_gather(opened rows), NCCL"}
+            def step_sharded(single=False):
+                tr = stark.generate_trace(raw0)
+                ios = syn.fill_outputs(raw0, tr.results(), stark.io_size, out_off)
+                pi = stark.generate_public_inputs(ios)
+                p = sbn.prove(stark, cfg, tr, pi) if single else sbn.prove_sharded(stark, cfg, tr, pi, rank, world, ag, allgather_device=agd)
+                tr.free()
+                sharded_phases.update(p.timings)
+                return p.to_bytes()
+            for _ in range(2):
+                sharded_bytes = step_sharded()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            nsh = 4
+            for _ in range(nsh):
+                sharded_bytes = step_sharded()
+            s1.record(stream)
+            barrier()
+            sh_ms = sharding.max_over_ranks([s0.elapsed_time(s1) / nsh], device="cuda")[0]
+            import hashlib
+            same = sharding.gather_digests({rank: sharded_bytes}, world, device="cuda")
+            ok = len({d[0] for d in same}) == 1
+            phases_sh = {k: round(v, 3) for k, v in sharded_phases.items()}
+            if rank == 0:
+                ok = ok and hashlib.sha256(step_sharded(single=True)).hexdigest() == same[0][0]
+            intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok, "phase_ms_rank0": phases_sh,
+                     "collectives": "NCCL all_gather: 3 x cap digests, opening values, opened rows (host-staged blocks); quotient values, FRI partial sums (device to device)"}
+        except Exception as e:   # noqa: BLE001
+            intra = {"world": world, "error": "%s: %s" % (type(e).__name__, e)}
 
     ms_total, e2e_ms = sharding.max_over_ranks([ms_total, e2e_s * 1000.0], device="cuda")
     # the only other cross-rank traffic: digests of the last proof of every rank (the "gather" of SURVEY §8e)
