@@ -112,7 +112,7 @@ int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, co
  * `allgather(user, send, nbytes, recv)` must deliver the `nbytes` of every rank, in rank order, into recv[world * nbytes] on
  * every rank (host memory; NCCL / gloo all_gather in the Python mirror) and return 0.  It is called the same number of times
  * with the same sizes on every rank: once per commitment (cap digests), once for the quotient values, once for the opened rows.
- * Needs rate_bits = 1 and world <= 2^cap_height.  world = 1 is sbn_prove. */
+ * Needs world <= 2^cap_height (any rate_bits).  world = 1 is sbn_prove. */
 typedef int (*sbn_allgather_fn)(void* user, const void* send, size_t nbytes, void* recv);
 /* `allgather_device` (optional, may be NULL): the same exchange on DEVICE buffers of this rank's GPU (ncclAllGather), used for
  * the quotient values so that they never pass through the host; the library has synchronised its stream before the call and

@@ -97,11 +97,13 @@ static void commit_from_coeffs(sbn_ctx* ctx, const Shard& sh, Commitment& c, int
   const size_t Lp = (N << rate_bits) >> sh.m;
   c.lde = DevBuf<u64>(ctx, (size_t)ncols * Lp);
   lde_class(ctx, c.coeffs, c.lde, ncols, logn, rate_bits, sh.m, sh.rho());
-  if (need_next && sh.world > 2) {
+  if (need_next && sh.world > 2 && rate_bits == 1) {   // rate 1: the quotient coset is the LDE coset, "next" rows = class rho + 2
     c.lde_next = DevBuf<u64>(ctx, (size_t)ncols * Lp);
     lde_class(ctx, c.coeffs, c.lde_next, ncols, logn, rate_bits, sh.m, (sh.rho() + 2) & (sh.world - 1));
   }
-  merkle_commit_lde(ctx, c.lde, ncols, logn + rate_bits - sh.m, 0, cap_height - sh.m, &c.tree);
+  // the class is laid out like a small LDE: [col][b'][k'] with B' = max(1, R / world) sub-cosets (lde_class)
+  const int l_logn = sh.m <= rate_bits ? logn : logn + rate_bits - sh.m, l_rate = sh.m <= rate_bits ? rate_bits - sh.m : 0;
+  merkle_commit_lde(ctx, c.lde, ncols, l_logn, l_rate, cap_height - sh.m, &c.tree);
   std::vector<uint8_t> all;
   sh.gather(c.tree.cap.data(), c.tree.cap.size() * 8, all);
   c.cap.resize(all.size() / 8);
@@ -161,7 +163,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   SBN_REQUIRE(total_arities <= logn + rate_bits - cap_height, "FRI total reduction arity is too large.");
   if (sh.on()) {
     SBN_REQUIRE(sh.allgather && (1 << sh.m) == sh.world && sh.rank >= 0 && sh.rank < sh.world, "sharded prove: world must be a power of two and the all-gather callback set");
-    SBN_REQUIRE(rate_bits == 1 && sh.m <= cap_height && sh.m < logn, "sharded prove: needs rate_bits = 1 and world <= 2^cap_height");
+    SBN_REQUIRE(sh.m <= cap_height && sh.m < logn, "sharded prove: world must not exceed 2^cap_height");
   }
   for (size_t i = 0; i < npis; i++) SBN_REQUIRE(public_inputs[i] < GL_P, "public input is not a canonical field element");
   PhaseTimer tm(ctx);
@@ -225,9 +227,25 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   } else {
     // this rank's class of the quotient coset (rate_bits = 1: the quotient coset is the LDE coset), then all classes -> [chal][bq][k]
     QDomain dom; dom.m = sh.m; dom.sigma = sh.rho();
-    dom.trace = trace_c.lde; dom.trace_next = sh.world > 2 ? trace_c.lde_next.get() : trace_c.lde.get();
-    if (uses_perm) { dom.zs = z_c.lde; dom.zs_next = sh.world > 2 ? z_c.lde_next.get() : z_c.lde.get(); }
     const size_t Mp = quotient_points(dom, logn);
+    DevBuf<u64> qt, qtn, qz, qzn;
+    if (rate_bits == 1) {   // the quotient coset is the LDE coset: the committed class batches are the quotient's inputs
+      dom.trace = trace_c.lde; dom.trace_next = sh.world > 2 ? trace_c.lde_next.get() : trace_c.lde.get();
+      if (uses_perm) { dom.zs = z_c.lde; dom.zs_next = sh.world > 2 ? z_c.lde_next.get() : z_c.lde.get(); }
+    } else {                // higher rates: the quotient coset is a sub-coset of the LDE coset that other ranks committed to;
+                            // evaluate this rank's class of it (and the class its "next" rows lie in) from the coefficients
+      const u32 nxt = (sh.rho() + 2) & (sh.world - 1);
+      qt = DevBuf<u64>(ctx, (size_t)trace_c.ncols * Mp);
+      lde_class(ctx, trace_c.coeffs, qt, trace_c.ncols, logn, 1, sh.m, sh.rho());
+      if (sh.world > 2) { qtn = DevBuf<u64>(ctx, (size_t)trace_c.ncols * Mp); lde_class(ctx, trace_c.coeffs, qtn, trace_c.ncols, logn, 1, sh.m, nxt); }
+      dom.trace = qt; dom.trace_next = sh.world > 2 ? qtn.get() : qt.get();
+      if (uses_perm) {
+        qz = DevBuf<u64>(ctx, (size_t)z_c.ncols * Mp);
+        lde_class(ctx, z_c.coeffs, qz, z_c.ncols, logn, 1, sh.m, sh.rho());
+        if (sh.world > 2) { qzn = DevBuf<u64>(ctx, (size_t)z_c.ncols * Mp); lde_class(ctx, z_c.coeffs, qzn, z_c.ncols, logn, 1, sh.m, nxt); }
+        dom.zs = qz; dom.zs_next = sh.world > 2 ? qzn.get() : qz.get();
+      }
+    }
     DevBuf<u64> acc_local(ctx, (size_t)SBN_MAX_CHALLENGES * Mp), acc_full(ctx, (size_t)nch * 2 * N);
     quotient_eval(ctx, air, dom, nullptr, nullptr, perm, d_pis, alphas, nch, logn, rate_bits, acc_local);
     if (sh.allgather_device) {   // device to device over NVLink, then one scatter kernel
@@ -380,7 +398,8 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     for (size_t q = 0; q < nq; q++) slot[q] = count[indices[q] >> logLp]++;
     size_t max_count = 0; for (size_t c : count) max_count = std::max(max_count, c);
     std::vector<u64> mine(rw_o * max_count, 0);
-    if (!local_idx.empty()) fri_gather_queries(ctx, qo, logLp, 0, {}, local_idx, mine.data());
+    const int l_logn = sh.m <= rate_bits ? logn : logLp, l_rate = sh.m <= rate_bits ? rate_bits - sh.m : 0;   // geometry of a class batch
+    if (!local_idx.empty()) fri_gather_queries(ctx, qo, l_logn, l_rate, {}, local_idx, mine.data());
     std::vector<uint8_t> all;
     sh.gather(mine.data(), mine.size() * 8, all);
     const u64* parts = reinterpret_cast<const u64*>(all.data());

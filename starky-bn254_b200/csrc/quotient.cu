@@ -210,7 +210,7 @@ void quotient_eval(sbn_ctx* ctx, const AirDesc& air, const QDomain& dom, const u
   SBN_REQUIRE(air.quotient_degree_factor() == 2, "only constraint_degree 3 (quotient degree factor 2) is supported");
   SBN_REQUIRE(rate_bits >= 1, "constraint degree higher than the rate is not supported");
   SBN_REQUIRE(num_challenges >= 1 && num_challenges <= SBN_MAX_CHALLENGES, "unsupported num_challenges");
-  SBN_REQUIRE(dom.m == 0 || (rate_bits == 1 && dom.m <= logn), "sharded quotient evaluation needs rate_bits = 1");
+  SBN_REQUIRE(dom.m <= logn, "too many quotient classes");
   const size_t N = size_t(1) << logn, R = size_t(1) << rate_bits, L = N * R;
   const size_t step = size_t(1) << (rate_bits - 1);
   const u64 w2n = gl_root_of_unity(logn + 1);

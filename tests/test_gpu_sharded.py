@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _sharded(sbn, world, make):
+def _sharded(sbn, world, make, rate_bits=1):
     """make(ctx) -> (stark, trace, public_inputs); returns the proof bytes of every rank."""
     from starky_bn254_b200 import sharding
     grp = sharding.ThreadGroup(world)
@@ -21,7 +21,8 @@ def _sharded(sbn, world, make):
         try:
             ctx = sbn.Context(0)
             stark, trace, pi = make(ctx)
-            out[rank] = sbn.prove_sharded(stark, stark.config(), trace, pi, rank, world, grp.allgather(rank)).to_bytes()
+            cfg = stark.config(); cfg.rate_bits = rate_bits
+            out[rank] = sbn.prove_sharded(stark, cfg, trace, pi, rank, world, grp.allgather(rank)).to_bytes()
             trace.free()
         except BaseException as e:
             err.append((rank, e))
@@ -91,13 +92,28 @@ def test_fq12_sharded_proof_is_byte_identical(ctx, sbn):
             assert got == want, (world, rank)
 
 
+@pytest.mark.parametrize("rate_bits,world", [(2, 2), (2, 4), (2, 8), (3, 2), (3, 8), (3, 16)])
+def test_modular_sharded_higher_rates(ctx, sbn, rate_bits, world):
+    """rate_bits 2 and 3 (BASELINE config 5): a rank's Merkle class is then several whole sub-cosets (world <= 2^rate_bits) or a
+    folded one, and its quotient class is evaluated separately from the coefficients; the proof must not change."""
+    n = 1024
+    ios = sbn.synthetic.modular_ios(n, seed=11)
+
+    def make(c):
+        stark = sbn.ModularStark(n, c)
+        return stark, stark.generate_trace(ios), np.zeros(0, dtype=np.uint64)
+
+    stark, trace, pi = make(ctx)
+    cfg = stark.config(); cfg.rate_bits = rate_bits
+    want = sbn.prove(stark, cfg, trace, pi).to_bytes()
+    for rank, got in enumerate(_sharded(sbn, world, make, rate_bits)):
+        assert got == want, (rate_bits, world, rank)
+
+
 def test_sharded_argument_errors(ctx, sbn):
     n = 512
     stark = sbn.ModularStark(n, ctx)
     trace = stark.generate_trace(sbn.synthetic.modular_ios(n))
-    cfg = stark.config(); cfg.rate_bits = 2
-    with pytest.raises(sbn.SbnError, match="rate_bits = 1"):
-        sbn.prove_sharded(stark, cfg, trace, np.zeros(0, dtype=np.uint64), 0, 2, lambda b: [b, b])
     with pytest.raises(sbn.SbnError, match="bad shard"):
         sbn.prove_sharded(stark, stark.config(), trace, np.zeros(0, dtype=np.uint64), 0, 3, lambda b: [b, b, b])
     # world = 1 is the plain prover (the callback is never used)

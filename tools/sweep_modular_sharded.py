@@ -3,7 +3,8 @@
 together through sbn_prove_sharded -- the LDE, the Merkle cap subtrees and the constraint evaluation are
 split by LDE class, the exchanges are NCCL all-gathers.  Rank 0 prints one JSON object per size: the sharded wall time per proof
 (max over ranks), the per-phase device milliseconds of rank 0, and -- when the trace fits -- the unsharded time on one GPU.
-    python -m torch.distributed.run --nproc-per-node N tools/sweep_modular_sharded.py [max_log_rows=20] [min_log_rows=18]"""
+    python -m torch.distributed.run --nproc-per-node N tools/sweep_modular_sharded.py [max_log_rows=20] [min_log_rows=18] [rates=1]
+(rates: comma-separated rate_bits; sizes whose LDE does not fit one GPU are proved sharded only)"""
 import hashlib
 import json
 import os
@@ -24,6 +25,7 @@ from sweep_modular import fast_ios  # noqa: E402
 def main():
     max_log = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     min_log = int(sys.argv[2]) if len(sys.argv) > 2 else 18
+    rates = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1]
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     json_fd = os.dup(1); os.dup2(2, 1)   # NCCL's banner goes to stderr
     torch.cuda.set_device(local)
@@ -40,36 +42,44 @@ def main():
         n = 1 << logn
         ios = fast_ios(n)
         stark = sbn.ModularStark(n, ctx)
-        cfg = stark.config()
-        res = {"rows_log2": logn, "rate_bits": 1, "world": world}
-        for mode in (["sharded"] if world > 1 else []) + ["single"]:
-            if mode == "single" and rank != 0:
-                continue
-            best = None
-            for rep in range(2):
-                tr = stark.generate_trace(ios)
-                ctx.synchronize()
-                if world > 1 and mode == "sharded":
-                    dist.barrier()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                proof = sbn.prove_sharded(stark, cfg, tr, empty, rank, world, ag, allgather_device=agd) if mode == "sharded" else sbn.prove(stark, cfg, tr, empty)
-                dt = (time.perf_counter() - t0) * 1e3
-                tr.free()
-                best = (dt, proof.timings, hashlib.sha256(proof.to_bytes()).hexdigest()[:16])
-            dt, ph, dig = best
-            if mode == "sharded":
-                dt = sharding.max_over_ranks([dt], device="cuda")[0]
-            res[mode + "_prove_ms"] = round(dt, 2)
-            res[mode + "_phases_rank0"] = {k: round(v, 2) for k, v in ph.items()}
-            res[mode + "_proof_sha"] = dig
-        if rank == 0:
-            if "sharded_prove_ms" in res:
-                res["identical"] = res["sharded_proof_sha"] == res["single_proof_sha"]
-                res["speedup"] = round(res["single_prove_ms"] / res["sharded_prove_ms"], 2)
-            os.write(json_fd, (json.dumps(res) + "\n").encode())
-        if world > 1:
-            dist.barrier()
+        for rate_bits in rates:
+            cfg = stark.config()
+            cfg.rate_bits = rate_bits
+            res = {"rows_log2": logn, "rate_bits": rate_bits, "world": world}
+            need_single = 8 * ((812 + 444 + 4) * (2 * n + (n << rate_bits)) + 2 * n * 24) * 1.15
+            modes = (["sharded"] if world > 1 else []) + (["single"] if need_single < 150e9 else [])
+            if need_single >= 150e9:
+                res["single_skipped"] = "needs %.0f GB of HBM on one GPU" % (need_single / 1e9)
+            for mode in modes:
+                if mode == "single" and rank != 0:
+                    continue
+                best = None
+                for rep in range(2):
+                    tr = stark.generate_trace(ios)
+                    ctx.synchronize()
+                    if world > 1 and mode == "sharded":
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    proof = sbn.prove_sharded(stark, cfg, tr, empty, rank, world, ag, allgather_device=agd) if mode == "sharded" else sbn.prove(stark, cfg, tr, empty)
+                    dt = (time.perf_counter() - t0) * 1e3
+                    tr.free()
+                    best = (dt, proof.timings, hashlib.sha256(proof.to_bytes()).hexdigest()[:16])
+                    del proof
+                dt, ph, dig = best
+                if mode == "sharded":
+                    dt = sharding.max_over_ranks([dt], device="cuda")[0]
+                    res["device_gb_per_rank"] = round(ctx.device_bytes / 1e9, 1)
+                res[mode + "_prove_ms"] = round(dt, 2)
+                res[mode + "_phases_rank0"] = {k: round(v, 2) for k, v in ph.items()}
+                res[mode + "_proof_sha"] = dig
+            if rank == 0:
+                if "sharded_prove_ms" in res and "single_prove_ms" in res:
+                    res["identical"] = res["sharded_proof_sha"] == res["single_proof_sha"]
+                    res["speedup"] = round(res["single_prove_ms"] / res["sharded_prove_ms"], 2)
+                os.write(json_fd, (json.dumps(res) + "\n").encode())
+            if world > 1:
+                dist.barrier()
     if world > 1:
         dist.destroy_process_group()
 
