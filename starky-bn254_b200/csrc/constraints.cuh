@@ -251,6 +251,25 @@ HD void eval_u16_range_check(QPoint& q, int start, int ntargets) {
   q.last_row(cur - F((1 << 16) - 1));
 }
 
+// The same constraint list cut into item ranges for small evaluation domains (quotient.cu k_segment_chunked): run 0 = the
+// `original - (lo + 256 hi)` constraints of targets [i0, i1), run 1 = their four lookup constraints each, run 2 = the three
+// table-column constraints that close the list.
+HD void eval_split_u16_range_check_run(QPoint& q, int main_col, int t0, int i0, int i1, int run) {
+  if (run == 0) {
+    for (int i = i0; i < i1; i++) {
+      F original = q.lv(t0 + i), lo = q.lv(main_col + 1 + 6 * i), hi = q.lv(main_col + 4 + 6 * i);
+      q.constraint(original - (lo + hi * F(1 << 8)));
+    }
+  } else if (run == 1) {
+    for (int i = main_col + 1 + 6 * i0; i < main_col + 1 + 6 * i1; i += 6) { eval_lookups(q, i + 1, i + 2); eval_lookups(q, i + 4, i + 5); }
+  } else {
+    F cur = q.lv(main_col), next = q.nv(main_col);
+    q.first_row(cur);
+    F incr = next - cur;
+    q.transition(incr * incr - incr);
+    q.last_row(cur - F((1 << 8) - 1));
+  }
+}
 // reference src/utils/range_check.rs:162-192 `eval_split_u16_range_check`: 5*ntargets + 3 constraints.
 HD void eval_split_u16_range_check(QPoint& q, int main_col, int t0, int ntargets) {
   for (int i = 0; i < ntargets; i++) {

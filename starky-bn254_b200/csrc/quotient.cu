@@ -53,6 +53,66 @@ HD void eval_permutation_checks(const QArgs& a, size_t idx, QPoint& q) {
   }
 }
 
+// runs of the same list over the Z range [z0, z1): run 0 = first-row constraints, run 1 = product constraints
+HD void eval_permutation_checks_run(const QArgs& a, size_t idx, QPoint& q, int z0, int z1, int run) {
+  const size_t M = size_t(1) << a.logm;
+  const int sg = (int)(idx >> a.logm);
+  const size_t k = idx & (M - 1), kn = (k + a.next_shift) & (M - 1);
+  const u64* zl = a.zs + a.seg_off[sg] + k;
+  const u64* zn = a.zs_next + a.seg_off[sg] + kn;
+  if (run == 0) {
+    for (int i = z0; i < z1; i++) q.first_row(F(zl[(size_t)i * a.zs_stride]) - F(1));
+    return;
+  }
+  for (int i = z0; i < z1; i++) {
+    F lhs(1), rhs(1);
+    for (int j = 0; j < a.perm_batch; j++) {
+      int e = i * a.perm_batch + j;
+      u32 l = a.perm_lhs[e];
+      if (l == 0xFFFFFFFFu) break;
+      F g(a.perm_gamma[e]);
+      lhs = lhs * (q.lv(l) + g);
+      rhs = rhs * (q.lv(a.perm_rhs[e]) + g);
+    }
+    q.constraint(F(zn[(size_t)i * a.zs_stride]) * rhs - F(zl[(size_t)i * a.zs_stride]) * lhs);
+  }
+}
+
+// Small evaluation domains (Fq12 at 2^13 rows, a rank's class of a sharded proof): one thread per point leaves most of the
+// GPU idle while each thread walks thousands of items (5 328 Z polynomials for Fq12).  The long item loops of the permutation
+// and split-range-check segments are cut into `nchunks` ranges (blockIdx.y); a chunk folds each of its runs with Horner from
+// zero and scales it by alpha^(number of constraints that follow the run in the full list), so that the sum over chunks is the
+// segment's Horner value S -- the same field element the one-thread-per-point kernel produces.
+struct ChunkPlan { int nchunks, nitems, per; };   // chunk j covers items [j per, min(nitems, (j + 1) per))
+__global__ void __launch_bounds__(128) k_segment_chunked(QArgs a, Segment s, ChunkPlan plan, const u64* __restrict__ weights /* [chunk][3][chal] */,
+                                                         u64* __restrict__ partial /* [chunk][chal][npoints] */) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= a.npoints) return;
+  const int ch = blockIdx.y, i0 = ch * plan.per, i1 = min(plan.nitems, i0 + plan.per);
+  QPoint q;
+  qpoint_begin(a, idx, q);
+  F total[SBN_MAX_CHALLENGES];
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) total[c] = F();
+  const int nruns = (s.kind == SEG_SPLIT_RANGE_CHECK && ch == plan.nchunks - 1) ? 3 : 2;
+  for (int run = 0; run < nruns; run++) {
+    for (int c = 0; c < SBN_MAX_CHALLENGES; c++) q.acc[c] = F();
+    if (s.kind == SEG_PERMUTATION) eval_permutation_checks_run(a, idx, q, i0, i1, run);
+    else eval_split_u16_range_check_run(q, s.p0, s.p1, i0, i1, run);
+    for (int c = 0; c < SBN_MAX_CHALLENGES; c++) total[c] = total[c] + q.acc[c] * F(weights[((size_t)ch * 3 + run) * SBN_MAX_CHALLENGES + c]);
+  }
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) partial[((size_t)ch * SBN_MAX_CHALLENGES + c) * a.npoints + idx] = f_canon(total[c]);
+}
+__global__ void k_combine_chunks(QArgs a, int nchunks, const u64* __restrict__ partial) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= a.npoints) return;
+  for (int c = 0; c < SBN_MAX_CHALLENGES; c++) {
+    u64* p = a.acc + (size_t)c * a.npoints + idx;
+    u64 v = a.first ? 0 : gl_mul(*p, a.alpha_m[c]);
+    for (int ch = 0; ch < nchunks; ch++) v = gl_add(v, partial[((size_t)ch * SBN_MAX_CHALLENGES + c) * a.npoints + idx]);
+    *p = v;
+  }
+}
+
 HD void eval_segment(const QArgs& a, const Segment& s, size_t idx, QPoint& q) {
   switch (s.kind) {
     case SEG_SPLIT_RANGE_CHECK: eval_split_u16_range_check(q, s.p0, s.p1, s.p2); break;
@@ -116,6 +176,30 @@ static const char* seg_name(SegKind k) {
 }
 static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
   unsigned blocks = (unsigned)((a.npoints + 127) / 128);
+  if ((s.kind == SEG_PERMUTATION || s.kind == SEG_SPLIT_RANGE_CHECK) && a.npoints <= (size_t(1) << 15)) {
+    // item ranges: enough chunks for ~2^18 threads, at least 16 items each
+    const int nitems = s.kind == SEG_PERMUTATION ? a.nz : s.p2;
+    int nchunks = (int)std::min<size_t>((size_t(1) << 18) / a.npoints, (size_t)std::max(1, nitems / 16));
+    if (nchunks > 1) {
+      ChunkPlan plan; plan.nitems = nitems; plan.per = (nitems + nchunks - 1) / nchunks; plan.nchunks = (nitems + plan.per - 1) / plan.per;
+      // constraints that follow each run of chunk j: permutation list = nz first-row + nz products; split list = n + 4 n + 3
+      std::vector<u64> w((size_t)plan.nchunks * 3 * SBN_MAX_CHALLENGES, 0);
+      for (int j = 0; j < plan.nchunks; j++) {
+        const u64 i1 = std::min(nitems, (j + 1) * plan.per), n = nitems;
+        u64 after[3];
+        if (s.kind == SEG_PERMUTATION) { after[0] = (n - i1) + n; after[1] = n - i1; after[2] = 0; }
+        else { after[0] = (n - i1) + 4 * n + 3; after[1] = 4 * (n - i1) + 3; after[2] = 0; }
+        for (int r = 0; r < 3; r++) for (int c = 0; c < SBN_MAX_CHALLENGES; c++) w[((size_t)j * 3 + r) * SBN_MAX_CHALLENGES + c] = gl_pow(a.alpha[c], after[r]);
+      }
+      DevBuf<u64> d_w(ctx, w.size()), partial(ctx, (size_t)plan.nchunks * SBN_MAX_CHALLENGES * a.npoints);
+      CUDA_CHECK(cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `w` is pageable host memory
+      KScope ks(ctx, seg_name(s.kind));
+      k_segment_chunked<<<dim3(blocks, plan.nchunks), 128, 0, ctx->stream>>>(a, s, plan, d_w, partial); LAUNCH_CHECK(ctx);
+      k_combine_chunks<<<blocks, 128, 0, ctx->stream>>>(a, plan.nchunks, partial); LAUNCH_CHECK(ctx);
+      return;
+    }
+  }
   if (s.kind == SEG_FQ12_MUL) {   // x = a; y = a (square) or b (mul): columns 0 / 192 of the row
     KScope kp(ctx, "q_fq12_products");
     k_fq12_products<<<dim3(blocks, 12), 128, 0, ctx->stream>>>(a, 0, s.p1 ? 0 : 192, a.scratch);
