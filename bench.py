@@ -22,8 +22,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 SAMPLE_SHIFT = 3
-WARP_INSTR_PER_PERM = 770.0      # ncu, k_leaf_hash of this build (profiles/r01_leaf_hash_ncu_summary_dp2a.txt)
-FMAHEAVY_BUSY_NCU = 0.857        # sm__pipe_fmaheavy_cycles_active of the same capture
+WARP_INSTR_PER_PERM = 766.0      # ncu, k_leaf_hash of this build: 21.06 G warp instructions / 27.5 M permutations (profiles/r01_leaf_hash_ncu_summary_final.txt)
+FMAHEAVY_BUSY_NCU = 0.817        # sm__pipe_fmaheavy_cycles_active of the same capture
 # --air selects the AIR; the headline (BASELINE.json configs[1], default) is g1.  (class, oracle id, num_io, input generator, metric, workload)
 AIRS = {
     "g1": ("G1ExpStark", 2, 128, "g1_exp_ios", "G1 scalar-mul STARK proofs/sec",
@@ -343,15 +343,15 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (Poseidon Merkle leaves)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     # ncu --set full capture of the trace-commitment launch (profiles/r01_leaf_hash_ncu_summary_dp2a.txt): dram read + write
-                     # 1.7605 GB + 10.7 MB = its algorithmic bytes (1676 columns x 2^17 rows x 8 B + digests): no re-reads.  G1 shape only.
-                     "traffic": 1.7712e9 if AIR == "g1" else None,
+                     # ncu --set full capture of the trace-commitment launch (profiles/r01_leaf_hash_ncu_summary_final.txt): dram read + write
+                     # 1.7639 GB + 10.0 MB = its algorithmic bytes (1676 columns x 2^17 rows x 8 B + digests): no re-reads.  G1 shape only.
+                     "traffic": 1.7740e9 if AIR == "g1" else None,
                      "traffic_note": "largest of the 3 launches per proof (trace commitment); `achieved` averages all 3 (trace, Z, quotient commitments)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "note": "kernel is bound by the integer multiplier (FMA-heavy) pipe, 86 %% busy under ncu (Poseidon ~ 2.5e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
+                     "note": "kernel is bound by the integer multiplier (FMA-heavy) pipe, 82 %% busy under ncu (Poseidon ~ 2.5e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
                      "share_of_kernel_time": leaf["ms"] / total_kernel_ms if total_kernel_ms else None},
         # integer-pipe view of the same kernel: ncu counts 770 warp instructions per permutation for this build (21.2 G warp
-        # instructions / 27.5 M permutations, profiles/r01_leaf_hash_ncu_summary_dp2a.txt); issue peak = 148 SMs x 4 schedulers x
+        # instructions / 27.5 M permutations, profiles/r01_leaf_hash_ncu_summary_final.txt); issue peak = 148 SMs x 4 schedulers x
         # 1 instr/clk x sm_max_mhz.  The binding unit is the multiplier pipe (sm__pipe_fmaheavy_cycles_active, ncu), not issue.
         "int_pipe": {"poseidon_perms_per_s": perms_per_proof * ksteps / (leaf["ms"] / 1e3) if leaf["ms"] else None, "perms_per_proof": perms_per_proof,
                      "warp_instr_per_perm": WARP_INSTR_PER_PERM,
