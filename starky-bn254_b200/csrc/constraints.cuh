@@ -511,10 +511,22 @@ HD void fq12_product_acc(const QPoint& q, int xa, int ya, int oi, F* acc /*31*/)
 #pragma unroll
           for (int t = 0; t < 16; t++) x[t] = -x[t];
         }
+#ifdef __CUDA_ARCH__
+        // one anti-diagonal at a time: up to 16 products summed unreduced in 160 bits (gl_acc), one reduction per coefficient
+        // instead of one per product
+#pragma unroll
+        for (int k = 0; k < 31; k++) {
+          gl_acc d = gl_acc_zero();
+#pragma unroll
+          for (int s = (k > 15 ? k - 15 : 0); s <= (k < 15 ? k : 15); s++) gl_acc_mac(d, x[s].v, y[k - s].v);
+          acc[k] = acc[k] + F(gl_acc_reduce(d));
+        }
+#else
 #pragma unroll
         for (int s = 0; s < 16; s++)
 #pragma unroll
           for (int t = 0; t < 16; t++) acc[s + t] = acc[s + t] + x[s] * y[t];
+#endif
       }
     }
   }

@@ -171,7 +171,9 @@ __device__ __forceinline__ u64 gl_add_nc2(u64 a, u64 b) {
 struct gl_acc { u64 lo, hi; u32 top; };
 __device__ __forceinline__ gl_acc gl_acc_zero() { gl_acc s; s.lo = 0; s.hi = 0; s.top = 0; return s; }
 __device__ __forceinline__ void gl_acc_mac(gl_acc& s, u64 a, u64 b) {
-  const u64 pl = a * b, ph = __umul64hi(a, b);
+  u32 x0, x1, x2, x3;
+  gl_mul128_words(a, b, x0, x1, x2, x3);   // four multiplications (the compiler's a * b + __umul64hi pair costs five and two IMAD)
+  const u64 pl = ((u64)x1 << 32) | x0, ph = ((u64)x3 << 32) | x2;
   asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(s.lo), "+l"(s.hi), "+r"(s.top) : "l"(pl), "l"(ph));
 }
 __device__ __forceinline__ u64 gl_sub_nc2(u64 a, u64 b);
