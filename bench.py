@@ -115,7 +115,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,9 +207,16 @@ def main():
         results = [None] * nslots
         errors = []
 
-        def work(slot):
+        nxt = iter(range(count))
+        lock = threading.Lock()
+
+        def work(slot):   # slots pull the next step as they finish one (no tail of idle slots when count % nslots != 0)
             try:
-                for i in range(slot, count, nslots):
+                while True:
+                    with lock:
+                        i = next(nxt, None)
+                    if i is None:
+                        return
                     results[slot] = fn(first + i, slot)
             except Exception as e:   # noqa: BLE001
                 errors.append(e)
