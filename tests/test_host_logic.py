@@ -298,3 +298,63 @@ def test_public_inputs_new_airs_match_oracle(sbn, orc):
         res = (np.arange(n * st.result_words, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(n, st.result_words)
         ios2 = syn.fill_outputs(ios, res, st.io_size, st.io_size - 8 * st.result_words)
         assert (st.generate_public_inputs(ios2) == orc.Air(air_id, n).generate_public_inputs(ios2)).all(), air_id
+
+
+def test_rust_sys_crate_declares_the_whole_c_abi():
+    """bindings/rust (not compiled here: no Rust toolchain) must declare every function of the C header, with the same number of
+    parameters, and every input record with the header's size."""
+    hdr = open(os.path.join(ROOT, "include", "starky_bn254_b200.h")).read()
+    rs = open(os.path.join(ROOT, "bindings", "rust", "starky-bn254-b200-sys", "src", "lib.rs")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_funcs = {m.group(1): m.group(2) for m in re.finditer(r"\b(sbn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr_nc) if "typedef" not in m.group(0)}
+    ext = rs[rs.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}\n")]
+    r_funcs = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (sbn_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]*)?;", ext, flags=re.S)}
+    nargs = lambda s: 0 if s.strip() in ("", "void") else s.count(",") + 1
+    assert set(c_funcs) == set(r_funcs), (sorted(set(c_funcs) - set(r_funcs)), sorted(set(r_funcs) - set(c_funcs)))
+    for name in c_funcs:
+        assert nargs(c_funcs[name]) == nargs(r_funcs[name]), name
+    for air, const in re.findall(r"(SBN_AIR_[A-Z0-9_]+) = (\d+)", hdr):
+        assert re.search(r"pub const %s: i32 = %s;" % (air, const), rs), air
+
+
+def test_wire_format_decodes_as_documented(orc, sbn):
+    """The proof wire format of DESIGN.md section 7, decoded the way bindings/rust `decode_proof` does it, on an oracle proof:
+    every byte is consumed and the shapes are those of StarkProofWithPublicInputs for ModularStark at 512 rows."""
+    n = 512
+    air = orc.Air(orc.AIR_MODULAR, n)
+    trace, _ = air.generate_trace(sbn.synthetic.modular_ios(n))
+    b = air.prove(trace, np.zeros(0, dtype=np.uint64))
+    at = 0
+
+    def u32():
+        nonlocal at
+        v = int.from_bytes(b[at:at + 4], "little"); at += 4
+        return v
+
+    def words(k):
+        nonlocal at
+        v = [int.from_bytes(b[at + 8 * i:at + 8 * i + 8], "little") for i in range(k)]; at += 8 * k
+        return v
+    hashes = lambda: words(4 * u32())
+    evec = lambda: words(2 * u32())
+    fvec = lambda: words(u32())
+    assert len(hashes()) == 64                      # trace cap: 16 digests
+    tag = b[at]; at += 1
+    assert tag == 1 and len(hashes()) == 64         # Option<permutation_zs_cap> = Some
+    assert len(hashes()) == 64                      # quotient cap
+    assert [len(evec()) // 2 for _ in range(5)] == [812, 812, 444, 444, 4]   # local, next, zs, zs_next, quotient
+    nlayers = u32()
+    assert nlayers == 1 and len(hashes()) == 64     # 2^9 rows: one arity-16 reduction
+    nq = u32()
+    assert nq == 84
+    for _ in range(nq):
+        assert u32() == 3
+        for ncols in (812, 444, 4):
+            assert len(fvec()) == ncols and len(hashes()) == 4 * (10 - 4)   # path up to (excluding) the cap level
+        assert u32() == nlayers
+        assert len(evec()) == 2 * 16 and len(hashes()) == 4 * (6 - 4)
+    assert len(evec()) == 2 * 32                    # final polynomial: 2^5 coefficients
+    pow_witness = words(1)[0]
+    assert pow_witness < P
+    assert fvec() == [] and at == len(b)            # no public inputs, nothing left
