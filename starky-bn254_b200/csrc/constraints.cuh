@@ -306,36 +306,49 @@ HD void eval_modular_stark_core(QPoint& q) {
 #define G1O_SIGN_Y 319
 
 // shared tail of eval_g1_add / eval_g1_double (muladd.rs:199-229 / :317-341)
-HD void eval_g1_tail(QPoint& q, F filter, int o, const F* lambda, const F* x1, const F* x2, const F* y1) {
-  F new_x[16], new_y[16];
-  load16(q, o + G1O_NEW_X, new_x); load16(q, o + G1O_NEW_Y, new_y);
-  // new_x_input = lambda^2 - (x1 + x2)
-  ModInput inx = mod_input1(lambda, lambda, 1, x1, x2);
-  eval_modular_op(q, filter, inx, new_x, o + G1O_AUX_X, o + G1O_SIGN_X);
-  // new_y_input = lambda * (x1 - new_x) - y1
-  F d[16];
-  for (int i = 0; i < 16; i++) d[i] = x1[i] - new_x[i];
-  ModInput iny = mod_input1(lambda, d, 1, y1);
-  eval_modular_op(q, filter, iny, new_y, o + G1O_AUX_Y, o + G1O_SIGN_Y);
+// `part`: 0 = the whole gadget; 1 / 2 / 3 = only its zero / new_x / new_y modular operation (consecutive runs of the constraint
+// list: the quotient kernel launches them as separate instantiations so that none carries the others' registers).
+HD void eval_g1_tail(QPoint& q, F filter, int o, const F* lambda, const F* x1, const F* x2, const F* y1, int part = 0) {
+  F new_x[16];
+  load16(q, o + G1O_NEW_X, new_x);
+  if (part == 0 || part == 2) {
+    // new_x_input = lambda^2 - (x1 + x2)
+    ModInput inx = mod_input1(lambda, lambda, 1, x1, x2);
+    eval_modular_op(q, filter, inx, new_x, o + G1O_AUX_X, o + G1O_SIGN_X);
+  }
+  if (part == 0 || part == 3) {
+    // new_y_input = lambda * (x1 - new_x) - y1
+    F d[16], new_y[16];
+    load16(q, o + G1O_NEW_Y, new_y);
+    for (int i = 0; i < 16; i++) d[i] = x1[i] - new_x[i];
+    ModInput iny = mod_input1(lambda, d, 1, y1);
+    eval_modular_op(q, filter, iny, new_y, o + G1O_AUX_Y, o + G1O_SIGN_Y);
+  }
 }
 // reference src/curves/g1/muladd.rs:179-230 `eval_g1_add`: 33 + 66 + 66 constraints.  a at cols 0..31, b at 32..63.
-HD void eval_g1_add(QPoint& q, F filter, int o) {
-  F ax[16], ay[16], bx[16], by[16], lambda[16], dx[16], dy[16];
-  load16(q, 0, ax); load16(q, 16, ay); load16(q, 32, bx); load16(q, 48, by); load16(q, o + G1O_LAMBDA, lambda);
-  for (int i = 0; i < 16; i++) { dx[i] = bx[i] - ax[i]; dy[i] = by[i] - ay[i]; }
-  // zero_pol = lambda * delta_x - delta_y
-  ModInput inz = mod_input1(lambda, dx, 1, dy);
-  eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
-  eval_g1_tail(q, filter, o, lambda, ax, bx, ay);
+HD void eval_g1_add(QPoint& q, F filter, int o, int part = 0) {
+  F ax[16], ay[16], bx[16], lambda[16];
+  load16(q, 0, ax); load16(q, 16, ay); load16(q, 32, bx); load16(q, o + G1O_LAMBDA, lambda);
+  if (part == 0 || part == 1) {
+    F by[16], dx[16], dy[16];
+    load16(q, 48, by);
+    for (int i = 0; i < 16; i++) { dx[i] = bx[i] - ax[i]; dy[i] = by[i] - ay[i]; }
+    // zero_pol = lambda * delta_x - delta_y
+    ModInput inz = mod_input1(lambda, dx, 1, dy);
+    eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
+  }
+  if (part != 1) eval_g1_tail(q, filter, o, lambda, ax, bx, ay, part);
 }
 // reference src/curves/g1/muladd.rs:291-342 `eval_g1_double`: 165 constraints.
-HD void eval_g1_double(QPoint& q, F filter, int o) {
+HD void eval_g1_double(QPoint& q, F filter, int o, int part = 0) {
   F x[16], y[16], lambda[16];
   load16(q, 0, x); load16(q, 16, y); load16(q, o + G1O_LAMBDA, lambda);
-  // zero_pol = 2*lambda*y - 3*x*x
-  ModInput inz = mod_input2(lambda, y, 2, x, x, -3);
-  eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
-  eval_g1_tail(q, filter, o, lambda, x, x, y);
+  if (part == 0 || part == 1) {
+    // zero_pol = 2*lambda*y - 3*x*x
+    ModInput inz = mod_input2(lambda, y, 2, x, x, -3);
+    eval_modular_zero(q, filter, inz, o + G1O_AUX_ZERO, o + G1O_SIGN_ZERO);
+  }
+  if (part != 1) eval_g1_tail(q, filter, o, lambda, x, x, y, part);
 }
 
 // ---- public-input binding of the exponentiation AIRs, folded over the instances ----
@@ -426,39 +439,49 @@ HD void eval_fq_mul(QPoint& q, F filter, bool square) {
 #define G2O_SIGN_ZERO 634
 #define G2O_SIGN 636
 // shared tail of eval_g2_add / eval_g2_double (muladd.rs:233-260 / :446-471): x1, y1 are the "a" operands
-HD void eval_g2_tail(QPoint& q, F filter, int o, const F* l0, const F* l1, const F* x1c0, const F* x1c1, const F* x2c0, const F* x2c1, const F* y1c0, const F* y1c1) {
-  F nx0[16], nx1[16], ny0[16], ny1[16];
+HD void eval_g2_tail(QPoint& q, F filter, int o, const F* l0, const F* l1, const F* x1c0, const F* x1c1, const F* x2c0, const F* x2c1, const F* y1c0, const F* y1c1,
+                     int part = 0) {
+  F nx0[16], nx1[16];
   load16(q, o + G2O_NEW_X, nx0); load16(q, o + G2O_NEW_X + 16, nx1);
-  // new_x_input = lambda^2 - (x1 + x2):  c0 = l0 l0 - l1 l1, c1 = l0 l1 + l1 l0
-  { ModInput in = mod_input2(l0, l0, 1, l1, l1, -1, x1c0, x2c0); eval_modular_op(q, filter, in, nx0, o + G2O_AUX, o + G2O_SIGN); }
-  { ModInput in = mod_input1(l0, l1, 2, x1c1, x2c1); eval_modular_op(q, filter, in, nx1, o + G2O_AUX + 95, o + G2O_SIGN + 1); }
-  // new_y_input = lambda * (x1 - new_x) - y1
-  F d0[16], d1[16];
-  for (int i = 0; i < 16; i++) { d0[i] = x1c0[i] - nx0[i]; d1[i] = x1c1[i] - nx1[i]; }
-  load16(q, o + G2O_NEW_Y, ny0); load16(q, o + G2O_NEW_Y + 16, ny1);
-  { ModInput in = mod_input2(l0, d0, 1, l1, d1, -1, y1c0); eval_modular_op(q, filter, in, ny0, o + G2O_AUX + 190, o + G2O_SIGN + 2); }
-  { ModInput in = mod_input2(l0, d1, 1, l1, d0, 1, y1c1); eval_modular_op(q, filter, in, ny1, o + G2O_AUX + 285, o + G2O_SIGN + 3); }
+  if (part == 0 || part == 2) {
+    // new_x_input = lambda^2 - (x1 + x2):  c0 = l0 l0 - l1 l1, c1 = l0 l1 + l1 l0
+    { ModInput in = mod_input2(l0, l0, 1, l1, l1, -1, x1c0, x2c0); eval_modular_op(q, filter, in, nx0, o + G2O_AUX, o + G2O_SIGN); }
+    { ModInput in = mod_input1(l0, l1, 2, x1c1, x2c1); eval_modular_op(q, filter, in, nx1, o + G2O_AUX + 95, o + G2O_SIGN + 1); }
+  }
+  if (part == 0 || part == 3) {
+    // new_y_input = lambda * (x1 - new_x) - y1
+    F d0[16], d1[16], ny0[16], ny1[16];
+    for (int i = 0; i < 16; i++) { d0[i] = x1c0[i] - nx0[i]; d1[i] = x1c1[i] - nx1[i]; }
+    load16(q, o + G2O_NEW_Y, ny0); load16(q, o + G2O_NEW_Y + 16, ny1);
+    { ModInput in = mod_input2(l0, d0, 1, l1, d1, -1, y1c0); eval_modular_op(q, filter, in, ny0, o + G2O_AUX + 190, o + G2O_SIGN + 2); }
+    { ModInput in = mod_input2(l0, d1, 1, l1, d0, 1, y1c1); eval_modular_op(q, filter, in, ny1, o + G2O_AUX + 285, o + G2O_SIGN + 3); }
+  }
 }
 // reference src/curves/g2/muladd.rs:416-472 `eval_g2_add`: 2*33 + 4*66 = 330 constraints
-HD void eval_g2_add(QPoint& q, F filter, int o) {
-  F ax0[16], ax1[16], ay0[16], ay1[16], bx0[16], bx1[16], l0[16], l1[16], dx0[16], dx1[16], dy0[16], dy1[16];
+HD void eval_g2_add(QPoint& q, F filter, int o, int part = 0) {
+  F ax0[16], ax1[16], ay0[16], ay1[16], bx0[16], bx1[16], l0[16], l1[16];
   load16(q, 0, ax0); load16(q, 16, ax1); load16(q, 32, ay0); load16(q, 48, ay1); load16(q, 64, bx0); load16(q, 80, bx1);
   load16(q, o + G2O_LAMBDA, l0); load16(q, o + G2O_LAMBDA + 16, l1);
-  for (int i = 0; i < 16; i++) { dx0[i] = bx0[i] - ax0[i]; dx1[i] = bx1[i] - ax1[i]; dy0[i] = q.lv(96 + i) - ay0[i]; dy1[i] = q.lv(112 + i) - ay1[i]; }
-  // zero_pol = lambda * delta_x - delta_y
-  { ModInput in = mod_input2(l0, dx0, 1, l1, dx1, -1, dy0); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO, o + G2O_SIGN_ZERO); }
-  { ModInput in = mod_input2(l0, dx1, 1, l1, dx0, 1, dy1); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO + 79, o + G2O_SIGN_ZERO + 1); }
-  eval_g2_tail(q, filter, o, l0, l1, ax0, ax1, bx0, bx1, ay0, ay1);
+  if (part == 0 || part == 1) {
+    F dx0[16], dx1[16], dy0[16], dy1[16];
+    for (int i = 0; i < 16; i++) { dx0[i] = bx0[i] - ax0[i]; dx1[i] = bx1[i] - ax1[i]; dy0[i] = q.lv(96 + i) - ay0[i]; dy1[i] = q.lv(112 + i) - ay1[i]; }
+    // zero_pol = lambda * delta_x - delta_y
+    { ModInput in = mod_input2(l0, dx0, 1, l1, dx1, -1, dy0); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO, o + G2O_SIGN_ZERO); }
+    { ModInput in = mod_input2(l0, dx1, 1, l1, dx0, 1, dy1); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO + 79, o + G2O_SIGN_ZERO + 1); }
+  }
+  if (part != 1) eval_g2_tail(q, filter, o, l0, l1, ax0, ax1, bx0, bx1, ay0, ay1, part);
 }
 // reference src/curves/g2/muladd.rs:203-261 `eval_g2_double`: 330 constraints
-HD void eval_g2_double(QPoint& q, F filter, int o) {
+HD void eval_g2_double(QPoint& q, F filter, int o, int part = 0) {
   F x0[16], x1[16], y0[16], y1[16], l0[16], l1[16];
   load16(q, 0, x0); load16(q, 16, x1); load16(q, 32, y0); load16(q, 48, y1);
   load16(q, o + G2O_LAMBDA, l0); load16(q, o + G2O_LAMBDA + 16, l1);
-  // zero_pol = 2 * lambda * y - 3 * x * x
-  { ModInput in = mod_input4(l0, y0, 2, l1, y1, -2, x0, x0, -3, x1, x1, 3); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO, o + G2O_SIGN_ZERO); }
-  { ModInput in = mod_input4(l0, y1, 2, l1, y0, 2, x0, x1, -3, x1, x0, -3); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO + 79, o + G2O_SIGN_ZERO + 1); }
-  eval_g2_tail(q, filter, o, l0, l1, x0, x1, x0, x1, y0, y1);
+  if (part == 0 || part == 1) {
+    // zero_pol = 2 * lambda * y - 3 * x * x
+    { ModInput in = mod_input4(l0, y0, 2, l1, y1, -2, x0, x0, -3, x1, x1, 3); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO, o + G2O_SIGN_ZERO); }
+    { ModInput in = mod_input4(l0, y1, 2, l1, y0, 2, x0, x1, -3, x1, x0, -3); eval_modular_zero(q, filter, in, o + G2O_AUX_ZERO + 79, o + G2O_SIGN_ZERO + 1); }
+  }
+  if (part != 1) eval_g2_tail(q, filter, o, l0, l1, x0, x1, x0, x1, y0, y1, part);
 }
 
 // ---- Fq12 (reference src/fields/fq12/mul.rs, src/fields/fq12/exp.rs, src/fields/fq12_u64) ----

@@ -164,6 +164,33 @@ template <int KIND> __global__ void __launch_bounds__(128) k_segment(QArgs a, Se
   qpoint_end(a, idx, q);
 }
 
+// The curve gadgets (zero / new_x / new_y modular operations: 33 + 66 + 66 constraints for G1, twice that for G2) as one
+// instantiation per operation: a third of the live limb arrays each (166 registers + 976 B of local arrays for the whole
+// G1 addition, 168 + 2 800 B for G2).
+template <int KIND, int PART> __global__ void __launch_bounds__(128) k_segment_part(QArgs a, Segment s) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= a.npoints) return;
+  QPoint q;
+  qpoint_begin(a, idx, q);
+  if (KIND == SEG_G1_ADD) eval_g1_add(q, q.lv(s.p1), s.p0, PART);
+  else if (KIND == SEG_G1_DOUBLE) eval_g1_double(q, q.lv(s.p1), s.p0, PART);
+  else if (KIND == SEG_G2_ADD) eval_g2_add(q, q.lv(s.p1), s.p0, PART);
+  else eval_g2_double(q, q.lv(s.p1), s.p0, PART);
+  qpoint_end(a, idx, q);
+}
+template <int KIND> static void launch_gadget_parts(sbn_ctx* ctx, const QArgs& a0, const Segment& s, unsigned blocks) {
+  const size_t unit = (KIND == SEG_G1_ADD || KIND == SEG_G1_DOUBLE) ? 33 : 66, m[3] = {unit, 2 * unit, 2 * unit};
+  QArgs a = a0;
+  for (int part = 1; part <= 3; part++) {
+    for (int c = 0; c < SBN_MAX_CHALLENGES; c++) a.alpha_m[c] = gl_pow(a.alpha[c], m[part - 1]);
+    if (part == 1) k_segment_part<KIND, 1><<<blocks, 128, 0, ctx->stream>>>(a, s);
+    else if (part == 2) k_segment_part<KIND, 2><<<blocks, 128, 0, ctx->stream>>>(a, s);
+    else k_segment_part<KIND, 3><<<blocks, 128, 0, ctx->stream>>>(a, s);
+    LAUNCH_CHECK(ctx);
+    a.first = 0;
+  }
+}
+
 static const char* seg_name(SegKind k) {
   switch (k) {
     case SEG_SPLIT_RANGE_CHECK: return "q_split_range_check"; case SEG_MODULAR_CORE: return "q_modular_core"; case SEG_G1_CORE: return "q_g1_core";
@@ -206,6 +233,10 @@ static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
     LAUNCH_CHECK(ctx);
   }
   KScope ks(ctx, seg_name(s.kind));
+  if (s.kind == SEG_G1_ADD) { launch_gadget_parts<SEG_G1_ADD>(ctx, a, s, blocks); return; }
+  if (s.kind == SEG_G1_DOUBLE) { launch_gadget_parts<SEG_G1_DOUBLE>(ctx, a, s, blocks); return; }
+  if (s.kind == SEG_G2_ADD) { launch_gadget_parts<SEG_G2_ADD>(ctx, a, s, blocks); return; }
+  if (s.kind == SEG_G2_DOUBLE) { launch_gadget_parts<SEG_G2_DOUBLE>(ctx, a, s, blocks); return; }
 #define SEGCASE(K) case K: k_segment<K><<<blocks, 128, 0, ctx->stream>>>(a, s); break;
   switch (s.kind) {
     SEGCASE(SEG_SPLIT_RANGE_CHECK) SEGCASE(SEG_MODULAR_CORE) SEGCASE(SEG_G1_CORE) SEGCASE(SEG_FLAGS) SEGCASE(SEG_G1_ADD)
