@@ -1,3 +1,5 @@
+# The ncu captures behind profiles/ (run on the GPU box: gpurun -- 'bash tools/profile_round.sh'): each capture only after the plain run
+# of the same command has exited 0; summaries are made here with tools/launch_list_summary.py, tools/kernel_table.py, tools/ncu_summary.py.
 set -x
 python tools/profile_g1.py 2 > gpurun_out/prof_plain_r1z.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_r1z.csv python tools/profile_g1.py 2 > gpurun_out/ncu_launch_r1z.log 2>&1
