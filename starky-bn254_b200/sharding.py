@@ -48,7 +48,10 @@ def gather_digests(local, num_batches, device="cpu"):
 
 def dist_allgather(group=None, device=None):
     """all-gather of equal-length byte strings over torch.distributed for `prove_sharded`: `device` = the rank's CUDA device
-    under NCCL (the bytes are staged through a device tensor so the transfer runs over NVLink), None under gloo."""
+    under NCCL (the bytes are staged through a device tensor so the transfer runs over NVLink), None under gloo.
+    The returned function also carries `.raw(send_ptr, nbytes, recv_ptr)`, which `prove_sharded` prefers: it works on the
+    library's host buffers in place (no Python-level copies; the opened rows of a wide AIR are megabytes per rank)."""
+    import ctypes
     world = dist.get_world_size(group)
 
     def allgather(data):
@@ -60,6 +63,17 @@ def dist_allgather(group=None, device=None):
         raw = out.cpu().numpy().tobytes()
         return [raw[i * len(data):(i + 1) * len(data)] for i in range(world)]
 
+    def raw(send_ptr, nbytes, recv_ptr):
+        s = torch.frombuffer((ctypes.c_ubyte * nbytes).from_address(send_ptr), dtype=torch.uint8)
+        r = torch.frombuffer((ctypes.c_ubyte * (nbytes * world)).from_address(recv_ptr), dtype=torch.uint8)
+        if device is None:
+            dist.all_gather_into_tensor(r, s, group=group)
+        else:
+            out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(out, s.to(device), group=group)
+            r.copy_(out)
+
+    allgather.raw = raw
     return allgather
 
 

@@ -64,6 +64,12 @@ def _allgather_worker(rank, world, port, q):
     for size in (32, 4096, 100001):          # cap digests, a mid-size block, an odd length
         parts = ag(bytes((rank * 7 + i) % 251 for i in range(size)))
         out.append([hashlib.sha256(x).hexdigest() for x in parts])
+        # the in-place form prove_sharded uses (library buffers, no Python-level copies) must deliver the same blocks
+        import ctypes
+        send = (ctypes.c_ubyte * size)(*[(rank * 7 + i) % 251 for i in range(size)])
+        recv = (ctypes.c_ubyte * (size * world))()
+        ag.raw(ctypes.addressof(send), size, ctypes.addressof(recv))
+        assert [hashlib.sha256(bytes(recv[r * size:(r + 1) * size])).hexdigest() for r in range(world)] == out[-1]
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, out))
