@@ -356,7 +356,13 @@ def main():
                      "traffic_note": "largest of the 3 launches per proof (trace commitment); `achieved` averages all 3 (trace, Z, quotient commitments)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                      "note": "kernel is bound by the integer multiplier (FMA-heavy) pipe, 82 %% busy under ncu (Poseidon ~ 2.5e4 integer ops per 64 B absorbed); see int_pipe. Kernel durations come from a serial pass of %d steps on one stream right after the timed region (overlapped proofs would blur per-kernel events)" % ksteps,
-                     "share_of_kernel_time": leaf["ms"] / total_kernel_ms if total_kernel_ms else None},
+                     "share_of_kernel_time": leaf["ms"] / total_kernel_ms if total_kernel_ms else None,
+                     # the roofline that actually binds this kernel: permutations/s against the rate at which the multiplier pipe
+                     # would be 100 % busy with this build's instruction mix (= achieved / pipe occupancy measured by ncu)
+                     "binding": {"bound": "integer multiplier (FMA-heavy) pipe", "unit": "Mperm/s",
+                                 "achieved": perms_per_proof * ksteps / (leaf["ms"] / 1e3) / 1e6 if leaf["ms"] else None,
+                                 "peak": perms_per_proof * ksteps / (leaf["ms"] / 1e3) / 1e6 / FMAHEAVY_BUSY_NCU if leaf["ms"] else None,
+                                 "frac": FMAHEAVY_BUSY_NCU, "source": "sm__pipe_fmaheavy_cycles_active, profiles/r01_leaf_hash_ncu_summary_final.txt"}},
         # integer-pipe view of the same kernel: ncu counts 770 warp instructions per permutation for this build (21.2 G warp
         # instructions / 27.5 M permutations, profiles/r01_leaf_hash_ncu_summary_final.txt); issue peak = 148 SMs x 4 schedulers x
         # 1 instr/clk x sm_max_mhz.  The binding unit is the multiplier pipe (sm__pipe_fmaheavy_cycles_active, ncu), not issue.
