@@ -106,6 +106,23 @@ class ThreadGroup:
         self.slots = [None] * world
         self.barrier = threading.Barrier(world)
 
+    def allgather_device(self, rank, device=0):
+        """Device-buffer all-gather between the threads (all contexts on `device`): every rank copies the published send
+        buffers into its own receive buffer with torch (views over the raw pointers), so the single-GPU tests exercise the same
+        library path NCCL serves in production (quotient values scattered on the device, column-split FRI reduction)."""
+        dev = torch.device("cuda", device)
+
+        def fn(send_ptr, nbytes, recv_ptr):
+            self.slots[rank] = (send_ptr, nbytes)
+            self.barrier.wait(timeout=600)
+            r = torch.as_tensor(_DevView(recv_ptr, nbytes * self.world), device=dev)
+            for k, (p, n) in enumerate(self.slots):
+                assert n == nbytes
+                r[k * nbytes:(k + 1) * nbytes].copy_(torch.as_tensor(_DevView(p, n), device=dev))
+            torch.cuda.synchronize(dev)
+            self.barrier.wait(timeout=600)
+        return fn
+
     def allgather(self, rank):
         def fn(data):
             self.slots[rank] = data

@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _sharded(sbn, world, make, rate_bits=1):
+def _sharded(sbn, world, make, rate_bits=1, device_exchange=False):
     """make(ctx) -> (stark, trace, public_inputs); returns the proof bytes of every rank."""
     from starky_bn254_b200 import sharding
     grp = sharding.ThreadGroup(world)
@@ -22,7 +22,8 @@ def _sharded(sbn, world, make, rate_bits=1):
             ctx = sbn.Context(0)
             stark, trace, pi = make(ctx)
             cfg = stark.config(); cfg.rate_bits = rate_bits
-            out[rank] = sbn.prove_sharded(stark, cfg, trace, pi, rank, world, grp.allgather(rank)).to_bytes()
+            agd = grp.allgather_device(rank) if device_exchange else None
+            out[rank] = sbn.prove_sharded(stark, cfg, trace, pi, rank, world, grp.allgather(rank), allgather_device=agd).to_bytes()
             trace.free()
         except BaseException as e:
             err.append((rank, e))
@@ -153,3 +154,35 @@ def test_gadget_airs_sharded_match_golden(sbn, golden, name, cls_name, gen):
 
     for rank, got in enumerate(_sharded(sbn, 4, make)):
         assert hashlib.sha256(got).hexdigest() == golden[name]["proof_sha256"], rank
+
+
+@pytest.mark.parametrize("world,rate_bits", [(2, 1), (8, 1), (4, 2)])
+def test_sharded_with_device_exchange(ctx, sbn, world, rate_bits):
+    """The device-buffer exchange path (NCCL all_gather on the library's buffers in production; torch copies between the threads'
+    buffers here): quotient values scattered by k_scatter_classes, FRI batch reduction split by columns."""
+    n = 1024
+    ios = sbn.synthetic.modular_ios(n, seed=21)
+
+    def make(c):
+        stark = sbn.ModularStark(n, c)
+        return stark, stark.generate_trace(ios), np.zeros(0, dtype=np.uint64)
+
+    stark, trace, pi = make(ctx)
+    cfg = stark.config(); cfg.rate_bits = rate_bits
+    want = sbn.prove(stark, cfg, trace, pi).to_bytes()
+    for rank, got in enumerate(_sharded(sbn, world, make, rate_bits, device_exchange=True)):
+        assert got == want, (world, rank)
+
+
+def test_g1_sharded_with_device_exchange_matches_golden(sbn, golden):
+    n = 128
+    syn = sbn.synthetic
+    ios = syn.g1_exp_ios(n)
+
+    def make(c):
+        stark = sbn.G1ExpStark(n, c)
+        trace = stark.generate_trace(ios)
+        return stark, trace, stark.generate_public_inputs(syn.fill_g1_outputs(ios, trace.results()))
+
+    for rank, got in enumerate(_sharded(sbn, 4, make, device_exchange=True)):
+        assert hashlib.sha256(got).hexdigest() == golden["g1_128"]["proof_sha256"], rank
