@@ -310,7 +310,7 @@ def main():
             if rank == 0:
                 ok = ok and hashlib.sha256(step_sharded(single=True)).hexdigest() == same[0][0]
             intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok, "phase_ms_rank0": phases_sh,
-                     "collectives": "NCCL all_gather: 3 x cap digests, opening values, opened rows (host-staged blocks); quotient values, FRI partial sums (device to device)"}
+                     "collectives": "NCCL all_gather: 3 x cap digests, opening values (host-staged blocks); quotient values, FRI partial sums, opened rows (device to device)"}
         except Exception as e:   # noqa: BLE001
             intra = {"world": world, "error": "%s: %s" % (type(e).__name__, e)}
 

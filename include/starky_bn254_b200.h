@@ -115,7 +115,7 @@ int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, co
  * Needs world <= 2^cap_height (any rate_bits).  world = 1 is sbn_prove. */
 typedef int (*sbn_allgather_fn)(void* user, const void* send, size_t nbytes, void* recv);
 /* `allgather_device` (optional, may be NULL): the same exchange on DEVICE buffers of this rank's GPU (ncclAllGather), used for
- * the quotient values so that they never pass through the host; the library has synchronised its stream before the call and
+ * the quotient values, the FRI partial sums and the opened rows so that they never pass through the host before the exchange; the library has synchronised its stream before the call and
  * the callback must return only when `recv` is complete.  NULL: the values are staged through host memory and `allgather`. */
 typedef struct { uint32_t rank, world; sbn_allgather_fn allgather; void* user; sbn_allgather_fn allgather_device; } sbn_shard;
 int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,

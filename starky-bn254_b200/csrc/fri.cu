@@ -334,7 +334,7 @@ size_t fri_query_record_words(const std::vector<QueryOracle>& oracles, const std
   return w;
 }
 void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, int logn, int rate_bits, const std::vector<FriLayer*>& layers,
-                        const std::vector<u64>& indices, u64* h_out) {
+                        const std::vector<u64>& indices, u64* h_out, u64* d_dst) {
   SBN_REQUIRE(oracles.size() <= 4 && layers.size() <= 8, "too many oracles / FRI layers");
   GatherDesc d; memset(&d, 0, sizeof d);
   d.noracles = (int)oracles.size(); d.nlayers = (int)layers.size(); d.logn = logn; d.rate_bits = rate_bits;
@@ -347,11 +347,12 @@ void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, i
     for (int l = 0; l < layers[j]->tree.num_levels(); l++) d.llevel_off[j][l] = layers[j]->tree.level_off[l];
   }
   size_t rw = fri_query_record_words(oracles, layers), nq = indices.size();
-  DevBuf<u64> d_idx(ctx, nq), d_out(ctx, nq * rw);
+  DevBuf<u64> d_idx(ctx, nq), d_own;
+  if (!d_dst) { d_own = DevBuf<u64>(ctx, nq * rw); d_dst = d_own; }
   CUDA_CHECK(cudaMemcpyAsync(d_idx, indices.data(), nq * 8, cudaMemcpyHostToDevice, ctx->stream));
   KScope ks(ctx, "fri_gather_queries");
-  k_gather_queries<<<(unsigned)nq, 256, 0, ctx->stream>>>(d, d_idx, rw, d_out);
+  k_gather_queries<<<(unsigned)nq, 256, 0, ctx->stream>>>(d, d_idx, rw, d_dst);
   LAUNCH_CHECK(ctx);
-  CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, nq * rw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (h_out) CUDA_CHECK(cudaMemcpyAsync(h_out, d_dst, nq * rw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `indices` may be a temporary of the caller
 }

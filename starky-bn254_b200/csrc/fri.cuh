@@ -33,4 +33,5 @@ struct QueryOracle { const u64* lde; int ncols; const DevMerkleTree* tree; };
 // Gathers all query openings into one flat u64 record per query (layout documented in fri.cu).
 size_t fri_query_record_words(const std::vector<QueryOracle>& oracles, const std::vector<FriLayer*>& layers);
 void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, int logn, int rate_bits, const std::vector<FriLayer*>& layers,
-                        const std::vector<u64>& indices, u64* h_out /* pinned or pageable host, nq * record_words */);
+                        const std::vector<u64>& indices, u64* h_out /* pinned or pageable host, nq * record_words; may be null */,
+                        u64* d_dst = nullptr /* optional device destination of the same shape (kept there for a device exchange) */);

@@ -397,11 +397,21 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     std::vector<size_t> count(sh.world, 0), slot(nq);
     for (size_t q = 0; q < nq; q++) slot[q] = count[indices[q] >> logLp]++;
     size_t max_count = 0; for (size_t c : count) max_count = std::max(max_count, c);
-    std::vector<u64> mine(rw_o * max_count, 0);
     const int l_logn = sh.m <= rate_bits ? logn : logLp, l_rate = sh.m <= rate_bits ? rate_bits - sh.m : 0;   // geometry of a class batch
-    if (!local_idx.empty()) fri_gather_queries(ctx, qo, l_logn, l_rate, {}, local_idx, mine.data());
     std::vector<uint8_t> all;
-    sh.gather(mine.data(), mine.size() * 8, all);
+    if (sh.allgather_device) {   // rows stay on the device until every rank has every block: one device-to-host copy
+      DevBuf<u64> d_mine(ctx, rw_o * max_count), d_all(ctx, rw_o * max_count * sh.world);
+      CUDA_CHECK(cudaMemsetAsync(d_mine, 0, rw_o * max_count * 8, ctx->stream));
+      if (!local_idx.empty()) fri_gather_queries(ctx, qo, l_logn, l_rate, {}, local_idx, nullptr, d_mine);
+      sh.gather_device(ctx, d_mine, rw_o * max_count * 8, d_all);
+      all.resize(rw_o * max_count * 8 * sh.world);
+      CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } else {
+      std::vector<u64> mine(rw_o * max_count, 0);
+      if (!local_idx.empty()) fri_gather_queries(ctx, qo, l_logn, l_rate, {}, local_idx, mine.data());
+      sh.gather(mine.data(), mine.size() * 8, all);
+    }
     const u64* parts = reinterpret_cast<const u64*>(all.data());
     for (size_t q = 0; q < nq; q++) memcpy(rec_o.data() + q * rw_o, parts + ((size_t)(indices[q] >> logLp) * max_count + slot[q]) * rw_o, rw_o * 8);
   }
