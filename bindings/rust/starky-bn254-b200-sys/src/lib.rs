@@ -9,6 +9,9 @@ use std::ptr;
 #[repr(C)] pub struct sbn_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct sbn_trace { _private: [u8; 0] }
 #[repr(C)] pub struct sbn_proof { _private: [u8; 0] }
+#[repr(C)] pub struct sbn_batch { _private: [u8; 0] }
+pub const SBN_BATCH_IOS_ON_DEVICE: u32 = 1;
+pub const SBN_BATCH_FILL_OUTPUTS: u32 = 2;
 
 /// `StarkConfig` (+ the coset shift, 0 = the field's multiplicative generator).
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)]
@@ -72,6 +75,13 @@ extern "C" {
                      out: *mut *mut sbn_proof) -> i32;
     pub fn sbn_prove_sharded(ctx: *mut sbn_ctx, config: *const sbn_config, trace: *const sbn_trace, public_inputs: *const u64, num_public_inputs: usize,
                              shard: *const sbn_shard, out: *mut *mut sbn_proof) -> i32;
+    pub fn sbn_batch_create(device: i32, lanes: u32, out: *mut *mut sbn_batch) -> i32;
+    pub fn sbn_batch_destroy(batch: *mut sbn_batch);
+    pub fn sbn_batch_last_error(batch: *const sbn_batch) -> *const c_char;
+    pub fn sbn_prove_batch(batch: *mut sbn_batch, air: i32, num_io: usize, config: *const sbn_config, ios: *const *const c_void, count: usize, flags: u32,
+                           proofs_out: *mut *mut sbn_proof) -> i32;
+    pub fn sbn_batch_launch_count(batch: *const sbn_batch) -> u64;
+    pub fn sbn_batch_device_bytes(batch: *const sbn_batch) -> u64;
     pub fn sbn_proof_serialize(proof: *const sbn_proof, buf: *mut u8, len: *mut usize) -> i32;
     pub fn sbn_proof_timings(proof: *const sbn_proof, buf: *mut c_char, cap: usize) -> i32;
     pub fn sbn_proof_debug(proof: *const sbn_proof, which: i32, out: *mut u64, cap_words: usize, written: *mut usize) -> i32;
@@ -99,17 +109,20 @@ impl Context {
     }
     fn check(&self, rc: i32) -> Result<(), SbnError> { if rc == 0 { Ok(()) } else { Err(SbnError { code: rc, message: unsafe { last_error(self.raw) } }) } }
     /// `stark.generate_trace(&inputs)` on the GPU; `ios` = the AIR's packed input records (`sbn_*_io`).
+    /// The record type must be the AIR's: its size is checked against `sbn_air_info` (the C side reads `io_size * num_io` bytes).
     pub fn generate_trace<T: Copy>(&self, air: i32, ios: &[T]) -> Result<Trace<'_>, SbnError> {
+        let info = air_info(air, ios.len())?;
+        if std::mem::size_of::<T>() != info.io_size { return Err(SbnError { code: -1, message: format!("record type is {} bytes, the AIR's input record is {}", std::mem::size_of::<T>(), info.io_size) }); }
         let mut t = ptr::null_mut();
         self.check(unsafe { sbn_trace_generate(self.raw, air, ios.as_ptr().cast(), ios.len(), &mut t) })?;
-        Ok(Trace { ctx: self, raw: t })
+        Ok(Trace { ctx: self, raw: t, result_words: info.result_words * ios.len() })
     }
     /// A trace made on the host (`Vec<PolynomialValues<F>>` flattened column-major, canonical u64 values).
     pub fn upload_trace(&self, air: i32, num_io: usize, cols: &[u64], ncols: usize, nrows: usize) -> Result<Trace<'_>, SbnError> {
         assert_eq!(cols.len(), ncols * nrows);
         let mut t = ptr::null_mut();
         self.check(unsafe { sbn_trace_upload(self.raw, air, num_io, cols.as_ptr(), ncols, nrows, &mut t) })?;
-        Ok(Trace { ctx: self, raw: t })
+        Ok(Trace { ctx: self, raw: t, result_words: 0 })
     }
     /// `starky::prover::prove`: returns the proof in the canonical wire format.
     pub fn prove(&self, config: &sbn_config, trace: &Trace<'_>, public_inputs: &[u64]) -> Result<Vec<u8>, SbnError> {
@@ -126,16 +139,62 @@ impl Context {
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { sbn_ctx_destroy(self.raw) } } }
 
-pub struct Trace<'a> { ctx: &'a Context, raw: *mut sbn_trace }
+pub struct Trace<'a> { ctx: &'a Context, raw: *mut sbn_trace, result_words: usize }
 impl Trace<'_> {
-    /// Per-instance chain results (G1: x, y as 8 words) to fill the `output` field of the input records.
-    pub fn results(&self, words: usize) -> Result<Vec<u64>, SbnError> {
-        let mut out = vec![0u64; words];
-        self.ctx.check(unsafe { sbn_trace_results(self.raw, out.as_mut_ptr()) })?;
+    /// Per-instance chain results (G1: x, y as 8 words each) to fill the `output` field of the input records:
+    /// `result_words * num_io` words, the size the C side writes (empty for an uploaded trace).
+    pub fn results(&self) -> Result<Vec<u64>, SbnError> {
+        let mut out = vec![0u64; self.result_words];
+        if self.result_words > 0 { self.ctx.check(unsafe { sbn_trace_results(self.raw, out.as_mut_ptr()) })?; }
         Ok(out)
     }
 }
 impl Drop for Trace<'_> { fn drop(&mut self) { unsafe { sbn_trace_free(self.raw) } } }
+
+/// `constants(num_io)` of an AIR (`sbn_air_info`).
+#[derive(Clone, Copy, Debug, Default)]
+pub struct AirInfo { pub num_columns: usize, pub num_public_inputs: usize, pub num_rows: usize, pub io_size: usize, pub result_words: usize, pub num_permutation_pairs: usize }
+pub fn air_info(air: i32, num_io: usize) -> Result<AirInfo, SbnError> {
+    let mut i = AirInfo::default();
+    let rc = unsafe { sbn_air_info(air, num_io, &mut i.num_columns, &mut i.num_public_inputs, &mut i.num_rows, &mut i.io_size, &mut i.result_words, &mut i.num_permutation_pairs) };
+    if rc != 0 { return Err(SbnError { code: rc, message: unsafe { last_error(ptr::null()) } }); }
+    Ok(i)
+}
+/// `stark.generate_public_inputs(&inputs)`; the record type is checked like in `Context::generate_trace`.
+pub fn public_inputs<T: Copy>(air: i32, ios: &[T]) -> Result<Vec<u64>, SbnError> {
+    let info = air_info(air, ios.len())?;
+    if std::mem::size_of::<T>() != info.io_size { return Err(SbnError { code: -1, message: "record type does not match the AIR".into() }); }
+    let mut out = vec![0u64; info.num_public_inputs];
+    let rc = unsafe { sbn_public_inputs(air, ios.as_ptr().cast(), ios.len(), out.as_mut_ptr(), out.len()) };
+    if rc != 0 { return Err(SbnError { code: rc, message: unsafe { last_error(ptr::null()) } }); }
+    Ok(out)
+}
+
+/// `lanes` worker contexts on one GPU sharing one set of device tables (`sbn_batch`): B independent proofs in one call.
+pub struct Batch { raw: *mut sbn_batch }
+unsafe impl Send for Batch {}
+impl Batch {
+    pub fn new(device: i32, lanes: u32) -> Result<Self, SbnError> {
+        let mut raw = ptr::null_mut();
+        let rc = unsafe { sbn_batch_create(device, lanes, &mut raw) };
+        if rc != 0 { return Err(SbnError { code: rc, message: unsafe { CStr::from_ptr(sbn_batch_last_error(ptr::null())).to_string_lossy().into_owned() } }); }
+        Ok(Batch { raw })
+    }
+    /// Trace generation + public inputs + prove for every element of `inputs` (each: the `num_io` records of one proof).
+    /// `fill_outputs`: take every record's `output` from the trace's chain result.  Returns the serialized proofs in order.
+    pub fn prove<T: Copy>(&self, air: i32, config: &sbn_config, inputs: &[&[T]], fill_outputs: bool) -> Result<Vec<Vec<u8>>, SbnError> {
+        if inputs.is_empty() { return Ok(vec![]); }
+        let num_io = inputs[0].len();
+        let info = air_info(air, num_io)?;
+        if std::mem::size_of::<T>() != info.io_size || inputs.iter().any(|x| x.len() != num_io) { return Err(SbnError { code: -1, message: "record type / batch shape does not match the AIR".into() }); }
+        let ptrs: Vec<*const c_void> = inputs.iter().map(|x| x.as_ptr().cast()).collect();
+        let mut proofs: Vec<*mut sbn_proof> = vec![ptr::null_mut(); inputs.len()];
+        let rc = unsafe { sbn_prove_batch(self.raw, air, num_io, config, ptrs.as_ptr(), ptrs.len(), if fill_outputs { SBN_BATCH_FILL_OUTPUTS } else { 0 }, proofs.as_mut_ptr()) };
+        if rc != 0 { return Err(SbnError { code: rc, message: unsafe { CStr::from_ptr(sbn_batch_last_error(self.raw)).to_string_lossy().into_owned() } }); }
+        Ok(proofs.into_iter().map(|p| unsafe { let mut len = 0usize; sbn_proof_serialize(p, ptr::null_mut(), &mut len); let mut b = vec![0u8; len]; sbn_proof_serialize(p, b.as_mut_ptr(), &mut len); sbn_proof_free(p); b }).collect())
+    }
+}
+impl Drop for Batch { fn drop(&mut self) { unsafe { sbn_batch_destroy(self.raw) } } }
 
 unsafe fn last_error(ctx: *const sbn_ctx) -> String { CStr::from_ptr(sbn_last_error(ctx)).to_string_lossy().into_owned() }
 pub fn standard_fast_config() -> sbn_config { let mut c = sbn_config::default(); unsafe { sbn_config_standard_fast(&mut c) }; c }

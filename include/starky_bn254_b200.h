@@ -17,6 +17,10 @@
 extern "C" {
 #endif
 
+/* Supported envelope (checked, SBN_ERR_INVALID otherwise): constraint degree 3 (quotient degree factor 2, as every AIR of the
+ * reference), 1 <= rate_bits <= 4, num_challenges <= 2, trace rows 2^8 .. 2^24 with rows << rate_bits <= 2^30, sharded world <= 16.
+ * Handle lifetime: a trace holds buffers of its context; sbn_ctx_destroy with live traces defers the destruction to the last
+ * sbn_trace_free.  Proofs are plain host objects and outlive their context. */
 typedef struct sbn_ctx sbn_ctx;     /* one per GPU / stream; not thread-safe, thread-compatible */
 typedef struct sbn_trace sbn_trace; /* device-resident, column-major trace (Vec<PolynomialValues<F>>) */
 typedef struct sbn_proof sbn_proof; /* StarkProofWithPublicInputs in the canonical wire format */
@@ -120,6 +124,29 @@ typedef int (*sbn_allgather_fn)(void* user, const void* send, size_t nbytes, voi
 typedef struct { uint32_t rank, world; sbn_allgather_fn allgather; void* user; sbn_allgather_fn allgather_device; } sbn_shard;
 int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, const uint64_t* public_inputs, size_t num_public_inputs,
                       const sbn_shard* shard, sbn_proof** out);
+/* Batched proofs ("batches of B independent G1 proofs"): `count` independent proofs of the same
+ * AIR in ONE call.  Replaces the loop a caller of the reference writes around
+ *     let trace = stark.generate_trace(&inputs); let pi = stark.generate_public_inputs(&inputs); prove(stark, &config, trace, pi, ..)
+ * (reference src/curves/g1/exp.rs:816-818, the five `*StarkyProofGenerator::run_once`, e.g. src/curves/g1/circuit.rs:187-201).
+ * A batch owns `lanes` worker contexts on one GPU (one CUDA stream, one device allocator and one host thread each) that share
+ * one set of read-only device tables; proofs are handed to the lanes as they become free, so the serial sections of one proof
+ * (exponentiation chains, lookup walk, host-side Fiat-Shamir) overlap with the wide kernels of the others, and the kernels of
+ * small traces (Fq12: 2^14 leaves) run concurrently.  Every proof is byte-identical to the one sbn_prove returns for the same
+ * inputs.  ios[j] points to the num_io input records of proof j (host memory, or device memory with SBN_BATCH_IOS_ON_DEVICE).
+ * SBN_BATCH_FILL_OUTPUTS: the `output` field of every record is taken from the trace (the chain result, sbn_trace_results)
+ * instead of being read from the caller's record -- the caller then need not compute the BN254 results natively first.
+ * proofs_out[count] receives the proofs (caller frees each with sbn_proof_free); on failure nothing is returned. */
+typedef struct sbn_batch sbn_batch;
+#define SBN_BATCH_IOS_ON_DEVICE 1u
+#define SBN_BATCH_FILL_OUTPUTS 2u
+int sbn_batch_create(int device, uint32_t lanes, sbn_batch** out);
+void sbn_batch_destroy(sbn_batch* batch);
+const char* sbn_batch_last_error(const sbn_batch* batch);
+int sbn_prove_batch(sbn_batch* batch, int air, size_t num_io, const sbn_config* config, const void* const* ios, size_t count, uint32_t flags,
+                    sbn_proof** proofs_out);
+uint64_t sbn_batch_launch_count(const sbn_batch* batch); /* kernels launched so far by all lanes */
+uint64_t sbn_batch_device_bytes(const sbn_batch* batch);  /* bytes held by the lanes' allocators */
+
 /* Canonical little-endian wire format (DESIGN.md "Proof wire format").  Call with buf == NULL to get the length. */
 int sbn_proof_serialize(const sbn_proof* proof, uint8_t* buf, size_t* len);
 /* JSON object of per-phase device milliseconds of the sbn_prove call that produced `proof` */

@@ -84,6 +84,15 @@ def lib():
         L.sbn_public_inputs.argtypes = [C.c_int, vp, sz, u64p, sz]
         L.sbn_prove.argtypes = [vp, vp, vp, u64p, sz, C.POINTER(vp)]
         L.sbn_prove_sharded.argtypes = [vp, vp, vp, u64p, sz, C.POINTER(Shard), C.POINTER(vp)]
+        L.sbn_batch_create.argtypes = [C.c_int, C.c_uint32, C.POINTER(vp)]
+        L.sbn_batch_destroy.argtypes = [vp]
+        L.sbn_batch_last_error.restype = C.c_char_p
+        L.sbn_batch_last_error.argtypes = [vp]
+        L.sbn_prove_batch.argtypes = [vp, C.c_int, sz, vp, C.POINTER(vp), sz, C.c_uint32, C.POINTER(vp)]
+        L.sbn_batch_launch_count.restype = C.c_uint64
+        L.sbn_batch_launch_count.argtypes = [vp]
+        L.sbn_batch_device_bytes.restype = C.c_uint64
+        L.sbn_batch_device_bytes.argtypes = [vp]
         L.sbn_proof_serialize.argtypes = [vp, vp, C.POINTER(sz)]
         L.sbn_proof_timings.argtypes = [vp, C.c_char_p, sz]
         L.sbn_proof_debug.argtypes = [vp, C.c_int, u64p, sz, C.POINTER(sz)]
@@ -198,9 +207,11 @@ class StarkProofWithPublicInputs:
 
     def __init__(self, ctx, handle):
         n = C.c_size_t()
-        ctx.check(lib().sbn_proof_serialize(handle, None, C.byref(n)))
+        if lib().sbn_proof_serialize(handle, None, C.byref(n)) != 0:
+            raise SbnError(-1, "sbn_proof_serialize failed")
         buf = C.create_string_buffer(n.value)
-        ctx.check(lib().sbn_proof_serialize(handle, buf, C.byref(n)))
+        if lib().sbn_proof_serialize(handle, buf, C.byref(n)) != 0:
+            raise SbnError(-1, "sbn_proof_serialize failed")
         self.bytes = buf.raw[:n.value]
         tb = C.create_string_buffer(4096)
         lib().sbn_proof_timings(handle, tb, 4096)
@@ -278,6 +289,8 @@ class _Stark:
         return Trace(c, h, self)
 
     def generate_public_inputs(self, inputs: bytes):
+        if len(inputs) != self.io_size * self.num_io:   # the C side reads io_size * num_io bytes
+            raise ValueError("inputs has the wrong length")
         out = np.zeros(max(self.num_public_inputs, 1), dtype=np.uint64)
         buf = C.create_string_buffer(bytes(inputs), len(inputs))
         rc = lib().sbn_public_inputs(self.AIR, buf, self.num_io, _ptr(out), self.num_public_inputs)
@@ -338,6 +351,67 @@ def prove(stark, config, trace, public_inputs, timing=None):
     if timing is not None:
         timing.update(proof.timings)
     return proof
+
+
+BATCH_IOS_ON_DEVICE, BATCH_FILL_OUTPUTS = 1, 2
+
+
+class Batch:
+    """sbn_batch: `lanes` worker contexts on one GPU (a CUDA stream, a device allocator and a native host thread each) sharing one
+    set of device tables.  `prove_batch` runs trace generation + prove for a list of independent input batches in ONE call
+    (SURVEY.md 8d config 2); the caller is a single host thread."""
+
+    def __init__(self, device=0, lanes=6):
+        self.h = C.c_void_p()
+        self.lanes = lanes
+        rc = lib().sbn_batch_create(device, lanes, C.byref(self.h))
+        if rc != 0:
+            raise SbnError(rc, lib().sbn_batch_last_error(None).decode())
+
+    @property
+    def launch_count(self):
+        return int(lib().sbn_batch_launch_count(self.h))
+
+    @property
+    def device_bytes(self):
+        return int(lib().sbn_batch_device_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().sbn_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prove_batch(stark, config, batch, inputs, on_device=False, fill_outputs=True):
+    """`count` independent proofs of `stark` in one call: for every element of `inputs` -- the packed input records of one proof,
+    as `bytes`, or a raw pointer (int) to host (pinned) or device memory -- trace generation, public inputs and prove.
+    fill_outputs: take each record's `output` field from the trace's chain result (sbn_trace_results) rather than from the record.
+    Returns the proofs in input order, each byte-identical to `prove`'s for the same inputs."""
+    n = len(inputs)
+    keep, ptrs = [], (C.c_void_p * n)()
+    for j, x in enumerate(inputs):
+        if isinstance(x, int):
+            ptrs[j] = x
+        else:
+            if on_device:
+                raise ValueError("device inputs must be raw pointers")
+            if len(x) != stark.io_size * stark.num_io:
+                raise ValueError("inputs has the wrong length")
+            buf = C.create_string_buffer(bytes(x), len(x))
+            keep.append(buf)
+            ptrs[j] = C.cast(buf, C.c_void_p).value
+    out = (C.c_void_p * n)()
+    flags = (BATCH_IOS_ON_DEVICE if on_device else 0) | (BATCH_FILL_OUTPUTS if fill_outputs else 0)
+    rc = lib().sbn_prove_batch(batch.h, stark.AIR, stark.num_io, C.byref(config), ptrs, n, flags, out)
+    if rc != 0:
+        raise SbnError(rc, lib().sbn_batch_last_error(batch.h).decode())
+    return [StarkProofWithPublicInputs(None, C.c_void_p(h)) for h in out]
 
 
 def prove_sharded(stark, config, trace, public_inputs, rank, world, allgather, timing=None, allgather_device=None):

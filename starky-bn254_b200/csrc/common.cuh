@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <tuple>
 #include <string>
 #include <vector>
@@ -29,19 +31,66 @@ struct NttTables {  // for domain size N = 2^logn: powers of w_N and w_N^-1 (N e
   int logn = 0; u64* w_fwd = nullptr; u64* w_inv = nullptr;
 };
 
+// Read-only device tables (twiddles, four-step factors, power tables) of one GPU.  A context owns its own set unless it was
+// created by a batch (sbn_batch_create), whose lanes share one: a table is built on the requesting context's stream, that
+// stream is synchronised, and only then is the pointer published under the mutex, so any other stream may read it.
+struct SharedTables {
+  std::mutex mu;
+  std::map<int, NttTables> ntt_tables;
+  std::map<std::tuple<int, bool, u64>, u64*> fourstep_tables;   // (logn, inverse, coset base) -> ntt.cu F table
+  std::map<std::pair<u64, int>, u64*> pow_tables;               // (base, logn) -> base^i, i < 2^logn
+  ~SharedTables() {
+    for (auto& kv : pow_tables) cudaFree(kv.second);
+    for (auto& kv : fourstep_tables) cudaFree(kv.second);
+  }
+};
+
 struct sbn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   int num_sms = 148;
   std::string last_error;
+  std::shared_ptr<SharedTables> tables = std::make_shared<SharedTables>();
+  unsigned ntt_attr_mask = 0;                      // sub-transform sizes whose kernels already have their shared-memory opt-in on this device
+  int live_handles = 0;                            // sbn_trace objects still holding buffers of this context
+  bool destroy_pending = false;                    // sbn_ctx_destroy was called with live handles: the last sbn_trace_free destroys
+  // Host waits: a blocking-sync event, so that a waiting host thread sleeps instead of spinning (a batch runs one host thread per
+  // lane and eight ranks share the box's cores).
+  cudaEvent_t sync_event = nullptr;
+  void sync() {
+    if (!sync_event) {
+      cudaError_t e0 = cudaEventCreateWithFlags(&sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+      if (e0 != cudaSuccess) throw SbnError(-2, std::string("cudaEventCreate: ") + cudaGetErrorString(e0));
+    }
+    cudaError_t e = cudaEventRecord(sync_event, stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(sync_event);
+    if (e != cudaSuccess) throw SbnError(-2, std::string("stream synchronisation: ") + cudaGetErrorString(e));
+  }
+  // Small host -> device uploads (challenge-dependent tables, descriptors) go through a pinned bump arena: a cudaMemcpyAsync from
+  // pageable memory first waits for everything queued on the stream.  The arena is rewound at the start of every entry point
+  // (nothing of the previous call is still in flight: every entry point ends with a host synchronisation).
+  uint8_t* pinned = nullptr; size_t pinned_cap = 0, pinned_used = 0;
+  void upload(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return;
+    const size_t need = (bytes + 63) & ~size_t(63);
+    if (!pinned) { pinned_cap = size_t(8) << 20; if (cudaMallocHost((void**)&pinned, pinned_cap) != cudaSuccess) { pinned = nullptr; pinned_cap = 0; cudaGetLastError(); } }
+    if (pinned_used + need > pinned_cap) {   // too large (or arena missing): plain copy, then wait so that `src` may die
+      cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) throw SbnError(-2, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e));
+      sync();
+      return;
+    }
+    memcpy(pinned + pinned_used, src, bytes);
+    cudaError_t e = cudaMemcpyAsync(dst, pinned + pinned_used, bytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) throw SbnError(-2, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e));
+    pinned_used += need;
+  }
+  void begin_call() { pinned_used = 0; }
   // caching allocator
   struct Block { void* p; size_t bytes; bool used; };
   std::vector<Block> blocks;
   size_t bytes_allocated = 0;
-  std::map<int, NttTables> ntt_tables;
-  std::map<std::tuple<int, bool, u64>, u64*> fourstep_tables;   // (logn, inverse, coset base) -> ntt.cu F table
-  std::map<std::pair<u64, int>, u64*> pow_tables;  // (base, logn) -> base^i, i < 2^logn
   unsigned long long launches = 0;                 // kernels launched by this library (bench: gpu_launches)
   // optional per-kernel-family CUDA-event timing on ctx->stream (bench.py roofline + breakdown)
   bool ktime_enabled = false;

@@ -179,7 +179,7 @@ void fri_final_poly(sbn_ctx* ctx, const std::vector<OracleView>& oracles, int lo
   }
   if (world > 1) {
     DevBuf<u64> all(ctx, (size_t)world * 4 * N);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
     split->gather_device(mine, 4 * N * 8, all);
     // comp1 = sum_r all[r][0], comp0 = comp1 + sum_r all[r][1]: the blocks are laid out as `2 world` partials of [2][N]
     k_sum_strided<<<(unsigned)((2 * N + 255) / 256), 256, 0, ctx->stream>>>(all, world, 4 * N, 0, 2 * N, comp1, nullptr); LAUNCH_CHECK(ctx);
@@ -270,14 +270,14 @@ u64 fri_pow_search(sbn_ctx* ctx, const u64 state[12], int pos, int pow_bits) {
   PowState st; memcpy(st.s, state, sizeof st.s);
   DevBuf<unsigned long long> best(ctx, 1);
   unsigned long long h = ~0ULL;
-  CUDA_CHECK(cudaMemcpyAsync(best, &h, 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->upload(best, &h, 8);
   const u64 batch = 1ULL << (pow_bits + 2 > 22 ? 22 : pow_bits + 2);
   for (u64 base = 0;; base += batch) {
     KScope ks(ctx, "fri_pow");
     k_pow<<<(unsigned)(batch / 128), 128, 0, ctx->stream>>>(st, pos, pow_bits, base, best);
     LAUNCH_CHECK(ctx);
     CUDA_CHECK(cudaMemcpyAsync(&h, best, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
     if (h != ~0ULL) return h;
     if (base + batch < base) throw SbnError(SBN_ERR_INTERNAL, "proof of work failed");
   }
@@ -349,10 +349,10 @@ void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, i
   size_t rw = fri_query_record_words(oracles, layers), nq = indices.size();
   DevBuf<u64> d_idx(ctx, nq), d_own;
   if (!d_dst) { d_own = DevBuf<u64>(ctx, nq * rw); d_dst = d_own; }
-  CUDA_CHECK(cudaMemcpyAsync(d_idx, indices.data(), nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->upload(d_idx, indices.data(), nq * 8);
   KScope ks(ctx, "fri_gather_queries");
   k_gather_queries<<<(unsigned)nq, 256, 0, ctx->stream>>>(d, d_idx, rw, d_dst);
   LAUNCH_CHECK(ctx);
   if (h_out) CUDA_CHECK(cudaMemcpyAsync(h_out, d_dst, nq * rw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `indices` may be a temporary of the caller
+  ctx->sync();   // `indices` may be a temporary of the caller
 }

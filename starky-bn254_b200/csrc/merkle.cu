@@ -73,7 +73,7 @@ void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t) {
   }
   t->cap.resize((size_t(4)) << t->cap_height);
   CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->digests + t->level_off.back(), t->cap.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
 }
 
 void merkle_leaf_hash_only(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int rate_bits, DevMerkleTree* t) {

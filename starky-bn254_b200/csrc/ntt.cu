@@ -16,27 +16,37 @@ __global__ void k_powers(u64* out, u64 base, size_t n) {
   if (i < n) out[i] = gl_pow(base, i);
 }
 
-const u64* get_pow_table(sbn_ctx* ctx, u64 base, int logn) {
+// Tables are built on the requesting context's stream and published (under the mutex of the table set, which the lanes of a
+// batch share) only after that stream has been synchronised, so every other stream may read them without further ordering.
+static const u64* pow_table_locked(sbn_ctx* ctx, u64 base, int logn) {
+  SharedTables& T = *ctx->tables;
   auto key = std::make_pair(base, logn);
-  auto it = ctx->pow_tables.find(key);
-  if (it != ctx->pow_tables.end()) return it->second;
+  auto it = T.pow_tables.find(key);
+  if (it != T.pow_tables.end()) return it->second;
   size_t n = size_t(1) << logn;
   u64* p; CUDA_CHECK(cudaMalloc(&p, n * 8));
   k_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, base, n);
   LAUNCH_CHECK(ctx);
-  ctx->pow_tables[key] = p;
+  ctx->sync();
+  T.pow_tables[key] = p;
   return p;
 }
+const u64* get_pow_table(sbn_ctx* ctx, u64 base, int logn) {
+  std::lock_guard<std::mutex> g(ctx->tables->mu);
+  return pow_table_locked(ctx, base, logn);
+}
 
-const NttTables& get_ntt_tables(sbn_ctx* ctx, int logn) {
-  auto it = ctx->ntt_tables.find(logn);
-  if (it != ctx->ntt_tables.end()) return it->second;
+NttTables get_ntt_tables(sbn_ctx* ctx, int logn) {
+  std::lock_guard<std::mutex> g(ctx->tables->mu);
+  SharedTables& T = *ctx->tables;
+  auto it = T.ntt_tables.find(logn);
+  if (it != T.ntt_tables.end()) return it->second;
   NttTables t; t.logn = logn;
   u64 w = gl_root_of_unity(logn);
-  t.w_fwd = (u64*)get_pow_table(ctx, w, logn);
-  t.w_inv = (u64*)get_pow_table(ctx, gl_inv(w), logn);
-  ctx->ntt_tables[logn] = t;
-  return ctx->ntt_tables[logn];
+  t.w_fwd = (u64*)pow_table_locked(ctx, w, logn);
+  t.w_inv = (u64*)pow_table_locked(ctx, gl_inv(w), logn);
+  T.ntt_tables[logn] = t;
+  return t;
 }
 
 // ---- in-shared-memory transform: mixed-radix decimation in frequency, up to radix 16 per pass ----
@@ -223,9 +233,11 @@ __global__ void k_fourstep_table(u64* __restrict__ out, u64 w, u64 c, u64 scale,
 }
 // (logn, inverse, coset base) -> F table (device, N entries), built once per context
 static const u64* get_fourstep_table(sbn_ctx* ctx, int logn, bool inverse, u64 c) {
+  std::lock_guard<std::mutex> g(ctx->tables->mu);
+  SharedTables& T = *ctx->tables;
   auto key = std::make_tuple(logn, inverse, c);
-  auto it = ctx->fourstep_tables.find(key);
-  if (it != ctx->fourstep_tables.end()) return it->second;
+  auto it = T.fourstep_tables.find(key);
+  if (it != T.fourstep_tables.end()) return it->second;
   const size_t n = size_t(1) << logn;
   const int l1 = logn / 2, l2 = logn - l1;
   u64 w = gl_root_of_unity(logn);
@@ -233,7 +245,8 @@ static const u64* get_fourstep_table(sbn_ctx* ctx, int logn, bool inverse, u64 c
   u64* p; CUDA_CHECK(cudaMalloc(&p, n * 8));
   k_fourstep_table<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, w, c ? c : 1, inverse ? gl_inv((u64)n) : 1, l2, n);
   LAUNCH_CHECK(ctx);
-  ctx->fourstep_tables[key] = p;
+  ctx->sync();
+  T.fourstep_tables[key] = p;
   return p;
 }
 
@@ -267,23 +280,22 @@ __global__ void k_ntt_small(const u64* __restrict__ in, size_t in_stride, u64* _
 // shared memory of a pass with sub-transform size 2^l: the tile (row stride T + 1) and the 2^l twiddles; 131 KB at l = 12
 static constexpr int ntt_tile_bytes(int l) { return (int)((((size_t)1 << l) * (((size_t)1 << ntt_logT_of(l)) + (ntt_logT_of(l) > 0 ? 1 : 0)) + ((size_t)1 << l)) * 8); }
 template <int L> static void launch_pass1(sbn_ctx* ctx, dim3 grid, size_t smem, bool pre, const u64* in, size_t in_stride, u64* tmp, const u64* W, const u64* F, const u64* P1, int l2) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the shared-memory opt-in is a per-device function attribute: remembered per context (a context is bound to one device)
+  if (!(ctx->ntt_attr_mask & (1u << L))) {
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_tile_bytes(L)));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_tile_bytes(L)));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass1<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    ctx->ntt_attr_mask |= 1u << L;
   }
   if (pre) k_ntt_pass1<L, true><<<grid, NTT_THREADS, smem, ctx->stream>>>(in, in_stride, tmp, W, F, P1, l2);
   else k_ntt_pass1<L, false><<<grid, NTT_THREADS, smem, ctx->stream>>>(in, in_stride, tmp, W, F, P1, l2);
 }
 template <int L> static void launch_pass2(sbn_ctx* ctx, dim3 grid, size_t smem, const u64* tmp, u64* out, size_t out_stride, const u64* W, const u64* postscale, int l1) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->ntt_attr_mask & (1u << (16 + L)))) {
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_tile_bytes(L)));
     CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass2<L>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    ctx->ntt_attr_mask |= 1u << (16 + L);
   }
   k_ntt_pass2<L><<<grid, NTT_THREADS, smem, ctx->stream>>>(tmp, out, out_stride, W, postscale, l1);
 }
@@ -299,7 +311,7 @@ void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t o
   if (ncols <= 0) return;
   SBN_REQUIRE(logn >= 1 && logn <= 24, "ntt: unsupported size");
   if (pre_base == 1) pre_base = 0;
-  const NttTables& tb = get_ntt_tables(ctx, logn);
+  const NttTables tb = get_ntt_tables(ctx, logn);
   const u64* W = inverse ? tb.w_inv : tb.w_fwd;
   const size_t N = size_t(1) << logn;
   if (logn <= 11) {

@@ -1,7 +1,7 @@
 #pragma once
 #include "common.cuh"
 const u64* get_pow_table(sbn_ctx* ctx, u64 base, int logn);
-const NttTables& get_ntt_tables(sbn_ctx* ctx, int logn);
+NttTables get_ntt_tables(sbn_ctx* ctx, int logn);
 void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int ncols, int logn, bool inverse,
                u64 pre_base, const u64* postscale);
 void intt_columns(sbn_ctx* ctx, const u64* values, u64* coeffs, int ncols, int logn);

@@ -12,9 +12,11 @@
 #include "fri.cuh"
 #include "tracegen.cuh"
 #include "poseidon.cuh"
+#include <atomic>
 #include <map>
 #include <memory>
 #include <sstream>
+#include <thread>
 
 // ------------------------------------------------------------------------------------------------
 // plonky2::iop::challenger::Challenger: duplex sponge in overwrite mode; challenges
@@ -73,7 +75,7 @@ struct Shard {
     if (rc != 0) throw SbnError(SBN_ERR_INTERNAL, "sharded prove: the all-gather callback failed");
   }
   void gather_device(sbn_ctx* ctx, const void* d_send, size_t nbytes, void* d_recv) const {   // device buffers, stream-ordered on both sides
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
     if (allgather_device(user, d_send, nbytes, d_recv) != 0) throw SbnError(SBN_ERR_INTERNAL, "sharded prove: the device all-gather callback failed");
   }
 };
@@ -204,7 +206,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     if (getenv("SBN_DEBUG_INTERMEDIATES")) {
       proof->dbg_z.resize(nz * N);
       CUDA_CHECK(cudaMemcpyAsync(proof->dbg_z.data(), zvals, nz * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->sync();
     }
     commit_from_values(ctx, sh, z_c, zvals, (int)nz, logn, rate_bits, cap_height, true);
     tm.mark("compute permutation Z commitments");
@@ -218,7 +220,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   u64 alphas[SBN_MAX_CHALLENGES] = {0, 0};
   for (int i = 0; i < nch; i++) alphas[i] = ch.get();
   DevBuf<u64> d_pis(ctx, npis ? npis : 1);
-  if (npis) CUDA_CHECK(cudaMemcpyAsync(d_pis, public_inputs, npis * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (npis) ctx->upload(d_pis, public_inputs, npis * 8);
   Commitment q_c;
   const int nq_polys = qdf * nch;
   q_c.coeffs = DevBuf<u64>(ctx, (size_t)nq_polys * N);
@@ -257,7 +259,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     } else {
       std::vector<u64> mine((size_t)nch * Mp), full((size_t)nch * 2 * N);
       CUDA_CHECK(cudaMemcpyAsync(mine.data(), acc_local, mine.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->sync();
       std::vector<uint8_t> all;
       sh.gather(mine.data(), mine.size() * 8, all);
       const u64* parts = reinterpret_cast<const u64*>(all.data());
@@ -270,7 +272,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
         }
       }
       CUDA_CHECK(cudaMemcpyAsync(acc_full, full.data(), full.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->sync();
     }
     quotient_finish(ctx, acc_full, nch, logn, q_c.coeffs);
   }
@@ -278,7 +280,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   if (getenv("SBN_DEBUG_INTERMEDIATES")) {
     proof->dbg_q.resize((size_t)nq_polys * N);
     CUDA_CHECK(cudaMemcpyAsync(proof->dbg_q.data(), q_c.coeffs, proof->dbg_q.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
   }
   commit_from_coeffs(ctx, sh, q_c, nq_polys, logn, rate_bits, cap_height, false);
   tm.mark("compute quotient commitment");
@@ -299,7 +301,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     if (Z) eval_columns_at_two_points(ctx, z_c.coeffs, Z, logn, zpw, d_open + (size_t)C * 4);
     eval_columns_at_two_points(ctx, q_c.coeffs, nq_polys, logn, zpw, d_open + (size_t)(C + Z) * 4);
     CUDA_CHECK(cudaMemcpyAsync(open.data(), d_open, open.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
   } else {
     // every rank evaluates its slice of the columns of each commitment; the values (4 words per column) are all-gathered
     const u64* cf[3] = {trace_c.coeffs.get(), Z ? z_c.coeffs.get() : nullptr, q_c.coeffs.get()};
@@ -314,7 +316,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
     }
     std::vector<u64> mine((size_t)tot_per * 4);
     CUDA_CHECK(cudaMemcpyAsync(mine.data(), d_mine, mine.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
     std::vector<uint8_t> all;
     sh.gather(mine.data(), mine.size() * 8, all);
     const u64* parts = reinterpret_cast<const u64*>(all.data());
@@ -367,7 +369,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   std::vector<u64> fa(nfinal), fb(nfinal), final_poly(2 * nfinal);
   CUDA_CHECK(cudaMemcpyAsync(fa.data(), cur_coeffs, nfinal * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync(fb.data(), cur_coeffs + (size_t(1) << cur_log), nfinal * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   for (size_t i = 0; i < nfinal; i++) { final_poly[2 * i] = fa[i]; final_poly[2 * i + 1] = fb[i]; }
   ch.observe_n(final_poly.data(), final_poly.size());
   tm.mark("fold codewords in the commitment phase");
@@ -406,7 +408,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
       sh.gather_device(ctx, d_mine, rw_o * max_count * 8, d_all);
       all.resize(rw_o * max_count * 8 * sh.world);
       CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->sync();
     } else {
       std::vector<u64> mine(rw_o * max_count, 0);
       if (!local_idx.empty()) fri_gather_queries(ctx, qo, l_logn, l_rate, {}, local_idx, mine.data());
@@ -446,42 +448,52 @@ static thread_local std::string g_create_error;
   return 0;
 
 extern "C" {
-int sbn_ctx_create(int device, void* cuda_stream, sbn_ctx** out) {
-  sbn_ctx* ctx = nullptr;
-  API_BEGIN
-  SBN_REQUIRE(out, "null output pointer");
+static sbn_ctx* ctx_new(int device, void* cuda_stream, std::shared_ptr<SharedTables> tables) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) throw SbnError(-2, std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
   SBN_REQUIRE(device >= 0 && device < ndev, "bad device index");
   CUDA_CHECK(cudaSetDevice(device));
-  sbn_ctx* c = new sbn_ctx();
+  std::unique_ptr<sbn_ctx> c(new sbn_ctx());   // nothing leaks if a later step throws
   c->device = device;
-  if (cuda_stream) c->stream = (cudaStream_t)cuda_stream; else { CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->owns_stream = true; }
+  if (tables) c->tables = tables;
   cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
-  *out = c;
-  API_END(ctx)
+  if (cuda_stream) c->stream = (cudaStream_t)cuda_stream; else { CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->owns_stream = true; }
+  return c.release();
 }
-void sbn_ctx_destroy(sbn_ctx* ctx) {
-  if (!ctx) return;
+static void ctx_delete(sbn_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->release_all();
   ctx->kresolve();
   for (auto e : ctx->kpool) cudaEventDestroy(e);
-  for (auto& kv : ctx->pow_tables) cudaFree(kv.second);
-  for (auto& kv : ctx->fourstep_tables) cudaFree(kv.second);
+  if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  delete ctx;   // the table set goes with its last owner
+}
+int sbn_ctx_create(int device, void* cuda_stream, sbn_ctx** out) {
+  sbn_ctx* ctx = nullptr;
+  API_BEGIN
+  SBN_REQUIRE(out, "null output pointer");
+  *out = ctx_new(device, cuda_stream, nullptr);
+  API_END(ctx)
+}
+void sbn_ctx_destroy(sbn_ctx* ctx) {
+  if (!ctx) return;
+  // traces hold buffers of this context's allocator: with live traces the destruction is deferred to the last sbn_trace_free
+  if (ctx->live_handles > 0) { ctx->destroy_pending = true; return; }
+  ctx_delete(ctx);
 }
 const char* sbn_last_error(const sbn_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
-int sbn_ctx_synchronize(sbn_ctx* ctx) { API_BEGIN CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); API_END(ctx) }
+int sbn_ctx_synchronize(sbn_ctx* ctx) { API_BEGIN SBN_REQUIRE(ctx, "null context"); CUDA_CHECK(cudaSetDevice(ctx->device)); ctx->sync(); API_END(ctx) }
 uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx) { return ctx->launches; }
 uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx) { return ctx->bytes_allocated; }
 
 int sbn_ctx_kernel_timing(sbn_ctx* ctx, int enable) {
   if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
   ctx->kresolve();
   ctx->ktime_enabled = enable != 0;
   ctx->kstats.clear();
@@ -489,6 +501,7 @@ int sbn_ctx_kernel_timing(sbn_ctx* ctx, int enable) {
 }
 int sbn_ctx_kernel_stats(sbn_ctx* ctx, char* buf, size_t cap) {
   if (!ctx || !buf || !cap) return -1;
+  cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->kresolve();
   std::ostringstream os; os << "{"; bool first = true;
@@ -520,11 +533,13 @@ static int trace_generate_impl(sbn_ctx* ctx, int air, const void* ios, bool on_d
   API_BEGIN
   SBN_REQUIRE(ctx && ios && out, "null argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->begin_call();
   std::unique_ptr<sbn_trace> t(new sbn_trace());
   t->ctx = ctx; t->air = make_air(air, num_io); t->logn = ilog2(t->air.num_rows);
   t->cols = DevBuf<u64>(ctx, t->air.num_columns * t->air.num_rows);
   t->results.resize(t->air.result_words * num_io);
   generate_trace(ctx, t->air, ios, on_device, t->cols, t->results.data());
+  ctx->live_handles++;
   *out = t.release();
   API_END(ctx)
 }
@@ -540,7 +555,8 @@ int sbn_trace_upload(sbn_ctx* ctx, int air, size_t num_io, const uint64_t* cols,
   t->logn = ilog2(nrows);
   t->cols = DevBuf<u64>(ctx, ncols * nrows);
   CUDA_CHECK(cudaMemcpyAsync(t->cols, cols, ncols * nrows * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
+  ctx->live_handles++;
   *out = t.release();
   API_END(ctx)
 }
@@ -548,8 +564,9 @@ int sbn_trace_download(const sbn_trace* t, uint64_t* cols_out) {
   sbn_ctx* ctx = t ? t->ctx : nullptr;
   API_BEGIN
   SBN_REQUIRE(t && cols_out, "null argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
   CUDA_CHECK(cudaMemcpyAsync(cols_out, t->cols, t->air.num_columns * t->air.num_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   API_END(ctx)
 }
 int sbn_trace_results(const sbn_trace* t, uint64_t* out) {
@@ -557,7 +574,13 @@ int sbn_trace_results(const sbn_trace* t, uint64_t* out) {
   memcpy(out, t->results.data(), t->results.size() * 8);
   return 0;
 }
-void sbn_trace_free(sbn_trace* t) { delete t; }
+void sbn_trace_free(sbn_trace* t) {
+  if (!t) return;
+  sbn_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
+  delete t;   // returns the buffer to the context's allocator
+  if (--ctx->live_handles == 0 && ctx->destroy_pending) ctx_delete(ctx);
+}
 
 int sbn_public_inputs(int air, const void* ios, size_t num_io, uint64_t* out, size_t out_len) {
   sbn_ctx* ctx = nullptr;
@@ -573,6 +596,7 @@ int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, co
   SBN_REQUIRE(ctx && config && trace && out && (public_inputs || num_public_inputs == 0), "null argument");
   SBN_REQUIRE(trace->ctx == ctx, "trace belongs to another context");
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->begin_call();
   std::unique_ptr<sbn_proof> p(new sbn_proof());
   prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, Shard(), p.get());
   *out = p.release();
@@ -587,11 +611,104 @@ int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* t
   CUDA_CHECK(cudaSetDevice(ctx->device));
   Shard sh; sh.rank = (int)shard->rank; sh.world = (int)shard->world; sh.allgather = shard->allgather; sh.user = shard->user; sh.allgather_device = shard->allgather_device;
   while ((1 << sh.m) < sh.world) sh.m++;
+  ctx->begin_call();
   std::unique_ptr<sbn_proof> p(new sbn_proof());
   prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, sh, p.get());
   *out = p.release();
   API_END(ctx)
 }
+// ---- batched proofs: a pool of lanes (context + host thread each) on one device sharing one table set ----
+struct sbn_batch {
+  int device = 0;
+  std::vector<sbn_ctx*> lanes;
+  std::string last_error;
+};
+int sbn_batch_create(int device, uint32_t lanes, sbn_batch** out) {
+  sbn_ctx* ctx = nullptr;
+  API_BEGIN
+  SBN_REQUIRE(out && lanes >= 1 && lanes <= 64, "sbn_batch_create: 1 <= lanes <= 64");
+  std::unique_ptr<sbn_batch> b(new sbn_batch());
+  b->device = device;
+  auto tables = std::make_shared<SharedTables>();
+  try {
+    for (uint32_t i = 0; i < lanes; i++) b->lanes.push_back(ctx_new(device, nullptr, tables));
+  } catch (...) { for (auto* c : b->lanes) ctx_delete(c); throw; }
+  *out = b.release();
+  API_END(ctx)
+}
+void sbn_batch_destroy(sbn_batch* b) {
+  if (!b) return;
+  for (auto* c : b->lanes) ctx_delete(c);
+  delete b;
+}
+const char* sbn_batch_last_error(const sbn_batch* b) { return b ? b->last_error.c_str() : g_create_error.c_str(); }
+uint64_t sbn_batch_launch_count(const sbn_batch* b) { uint64_t n = 0; if (b) for (auto* c : b->lanes) n += c->launches; return n; }
+uint64_t sbn_batch_device_bytes(const sbn_batch* b) { uint64_t n = 0; if (b) for (auto* c : b->lanes) n += c->bytes_allocated; return n; }
+
+// one proof on one lane: K1, public inputs, K2-K6
+static void batch_job(sbn_ctx* ctx, const AirDesc& air, const sbn_config& cfg, const void* ios, uint32_t flags, sbn_proof* proof) {
+  const bool on_device = (flags & SBN_BATCH_IOS_ON_DEVICE) != 0;
+  ctx->begin_call();
+  sbn_trace t;
+  t.ctx = ctx; t.air = air; t.logn = ilog2(air.num_rows);
+  t.cols = DevBuf<u64>(ctx, air.num_columns * air.num_rows);
+  t.results.resize(air.result_words * air.num_io);
+  generate_trace(ctx, air, ios, on_device, t.cols, t.results.data());
+  std::vector<u64> pis(air.num_public_inputs);
+  if (air.num_public_inputs) {
+    const size_t bytes = air.io_size * air.num_io;
+    std::vector<uint8_t> host;
+    const void* recs = ios;
+    if (on_device || (flags & SBN_BATCH_FILL_OUTPUTS)) {
+      host.resize(bytes);
+      if (on_device) { CUDA_CHECK(cudaMemcpyAsync(host.data(), ios, bytes, cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
+      else memcpy(host.data(), ios, bytes);
+      if (flags & SBN_BATCH_FILL_OUTPUTS) {   // output = the chain result: the trailing result_words u64 of every record
+        const size_t rb = air.result_words * 8;
+        for (size_t i = 0; i < air.num_io; i++) memcpy(host.data() + (i + 1) * air.io_size - rb, t.results.data() + i * air.result_words, rb);
+      }
+      recs = host.data();
+    }
+    format_public_inputs(air, recs, pis.data());
+  }
+  prove_impl(ctx, cfg, &t, pis.data(), pis.size(), Shard(), proof);
+}
+int sbn_prove_batch(sbn_batch* b, int air_id, size_t num_io, const sbn_config* config, const void* const* ios, size_t count, uint32_t flags,
+                    sbn_proof** proofs_out) {
+  if (!b) return SBN_ERR_INVALID;
+  try {
+    SBN_REQUIRE(config && ios && proofs_out, "null argument");
+    const AirDesc air = make_air(air_id, num_io);
+    for (size_t j = 0; j < count; j++) { SBN_REQUIRE(ios[j], "null input batch"); proofs_out[j] = nullptr; }
+    std::vector<std::unique_ptr<sbn_proof>> proofs(count);
+    std::atomic<size_t> next(0);
+    std::atomic<bool> failed(false);
+    std::mutex err_mu; std::string err; int err_code = 0;
+    auto work = [&](sbn_ctx* ctx) {
+      try {
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        for (;;) {
+          const size_t j = next.fetch_add(1);
+          if (j >= count || failed.load()) return;
+          std::unique_ptr<sbn_proof> p(new sbn_proof());
+          batch_job(ctx, air, *config, ios[j], flags, p.get());
+          proofs[j] = std::move(p);
+        }
+      } catch (const SbnError& e) { failed = true; std::lock_guard<std::mutex> g(err_mu); if (!err_code) { err_code = e.code; err = e.what(); } }
+      catch (const std::exception& e) { failed = true; std::lock_guard<std::mutex> g(err_mu); if (!err_code) { err_code = SBN_ERR_INTERNAL; err = e.what(); } }
+    };
+    const size_t nworkers = std::min(b->lanes.size(), count);
+    std::vector<std::thread> threads;
+    for (size_t w = 1; w < nworkers; w++) threads.emplace_back(work, b->lanes[w]);
+    if (nworkers) work(b->lanes[0]);   // the calling thread drives lane 0
+    for (auto& t : threads) t.join();
+    if (err_code) { b->last_error = err; return err_code; }
+    for (size_t j = 0; j < count; j++) proofs_out[j] = proofs[j].release();
+  } catch (const SbnError& e) { b->last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { b->last_error = e.what(); return SBN_ERR_INTERNAL; }
+  return 0;
+}
+
 int sbn_proof_serialize(const sbn_proof* proof, uint8_t* buf, size_t* len) {
   if (!proof || !len) return -1;
   if (!buf) { *len = proof->bytes.size(); return 0; }
@@ -629,12 +746,13 @@ int sbn_poseidon_permute(sbn_ctx* ctx, uint64_t* states, size_t n) {
   API_BEGIN
   SBN_REQUIRE(ctx && states, "null argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->begin_call();
   DevBuf<u64> d(ctx, n * 12);
   CUDA_CHECK(cudaMemcpyAsync(d, states, n * 96, cudaMemcpyHostToDevice, ctx->stream));
   k_poseidon_batch<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d, n);
   LAUNCH_CHECK(ctx);
   CUDA_CHECK(cudaMemcpyAsync(states, d, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   API_END(ctx)
 }
 
@@ -650,6 +768,7 @@ int sbn_commit_columns(sbn_ctx* ctx, const uint64_t* values, size_t ncols, int l
   API_BEGIN
   SBN_REQUIRE(ctx && values && ncols > 0, "null argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->begin_call();
   size_t N = size_t(1) << logn, L = N << rate_bits;
   DevBuf<u64> d_vals(ctx, ncols * N);
   CUDA_CHECK(cudaMemcpyAsync(d_vals, values, ncols * N * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -661,10 +780,10 @@ int sbn_commit_columns(sbn_ctx* ctx, const uint64_t* values, size_t ncols, int l
     k_lde_to_natural<<<(unsigned)((ncols * L + 255) / 256), 256, 0, ctx->stream>>>(c.lde, nat, logn, rate_bits, ncols);
     LAUNCH_CHECK(ctx);
     CUDA_CHECK(cudaMemcpyAsync(lde_out, nat, ncols * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sync();
   }
   if (cap_out) memcpy(cap_out, c.tree.cap.data(), c.tree.cap.size() * 8);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   API_END(ctx)
 }
 
@@ -678,6 +797,7 @@ int sbn_bench_commit(sbn_ctx* ctx, size_t ncols, int logn, int rate_bits, int ca
   API_BEGIN
   SBN_REQUIRE(ctx && ms && iters > 0, "bad argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->begin_call();
   size_t N = size_t(1) << logn, L = N << rate_bits;
   DevBuf<u64> vals(ctx, ncols * N), coeffs(ctx, ncols * N), lde(ctx, ncols * L);
   k_fill_pseudo<<<(unsigned)((ncols * N + 255) / 256), 256, 0, ctx->stream>>>(vals, ncols * N);

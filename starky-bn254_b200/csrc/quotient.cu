@@ -219,8 +219,7 @@ static void launch_segment(sbn_ctx* ctx, const QArgs& a, const Segment& s) {
         for (int r = 0; r < 3; r++) for (int c = 0; c < SBN_MAX_CHALLENGES; c++) w[((size_t)j * 3 + r) * SBN_MAX_CHALLENGES + c] = gl_pow(a.alpha[c], after[r]);
       }
       DevBuf<u64> d_w(ctx, w.size()), partial(ctx, (size_t)plan.nchunks * SBN_MAX_CHALLENGES * a.npoints);
-      CUDA_CHECK(cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `w` is pageable host memory
+      ctx->upload(d_w, w.data(), w.size() * 8);
       KScope ks(ctx, seg_name(s.kind));
       k_segment_chunked<<<dim3(blocks, plan.nchunks), 128, 0, ctx->stream>>>(a, s, plan, d_w, partial); LAUNCH_CHECK(ctx);
       k_combine_chunks<<<blocks, 128, 0, ctx->stream>>>(a, plan.nchunks, partial); LAUNCH_CHECK(ctx);
@@ -285,11 +284,10 @@ static void build_pi_binding(sbn_ctx* ctx, QArgs& a, const QDomain& dom, const S
     a.pi_skip[c] = ha[(size_t)c * num_io];                                                            // alpha^((n-1) io_len)
   }
   DevBuf<u64> d_a(ctx, ha.size()), vals(ctx, (size_t)ncols * N), coeffs(ctx, (size_t)ncols * N);
-  CUDA_CHECK(cudaMemcpyAsync(d_a, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->upload(d_a, ha.data(), ha.size() * 8);
   CUDA_CHECK(cudaMemsetAsync(vals, 0, (size_t)ncols * N * 8, ctx->stream));
   k_pi_columns<<<dim3((per + 63) / 64, num_io), 64, 0, ctx->stream>>>(vals, N, d_public_inputs, d_a, num_io, rows_per_io, group_count, num_challenges);
   LAUNCH_CHECK(ctx);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `ha` is pageable host memory
   intt_columns(ctx, vals, coeffs, ncols, logn);
   lde = DevBuf<u64>(ctx, (size_t)ncols * a.npoints);
   lde_class(ctx, coeffs, lde, ncols, logn, 1, dom.m, dom.sigma);   // m = 0: both half-cosets, [col][bq][k]
@@ -359,10 +357,9 @@ void quotient_eval(sbn_ctx* ctx, const AirDesc& air, const QDomain& dom, const u
   if (perm.nz()) {
     size_t ne = perm.lhs.size();
     d_lhs = DevBuf<u32>(ctx, ne); d_rhs = DevBuf<u32>(ctx, ne); d_gamma = DevBuf<u64>(ctx, ne);
-    CUDA_CHECK(cudaMemcpyAsync(d_lhs, perm.lhs.data(), ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(d_rhs, perm.rhs.data(), ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(d_gamma, perm.gamma.data(), ne * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // host vectors may die before the copy runs otherwise
+    ctx->upload(d_lhs, perm.lhs.data(), ne * 4);
+    ctx->upload(d_rhs, perm.rhs.data(), ne * 4);
+    ctx->upload(d_gamma, perm.gamma.data(), ne * 8);
     a.perm_lhs = d_lhs; a.perm_rhs = d_rhs; a.perm_gamma = d_gamma; a.perm_batch = perm.batch_size; a.nz = (int)perm.nz();
     segs.push_back({SEG_PERMUTATION, 0, 0, 0, 0, 2 * perm.nz()});
   }

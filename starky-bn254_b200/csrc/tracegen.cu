@@ -186,8 +186,7 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
   size_t group = std::max<size_t>(1, (size_t(512) << 20) / per);
   group = std::min(group, descs.size());
   DevBuf<LookupDesc> d_desc(ctx, descs.size());
-  CUDA_CHECK(cudaMemcpyAsync(d_desc, descs.data(), descs.size() * sizeof(LookupDesc), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->upload(d_desc, descs.data(), descs.size() * sizeof(LookupDesc));
   // SBN_LOOKUP_SEQUENTIAL=1 selects the one-value-per-step kernel (k_lookup_walk), kept as the in-library cross-check of the
   // chunked kernel (tests/test_gpu_parity.py compares the two on skewed and uniform columns).
   const bool sequential = getenv("SBN_LOOKUP_SEQUENTIAL") != nullptr;
@@ -209,7 +208,7 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
   }
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   SBN_REQUIRE(!h_err, "range-checked column holds a value >= 2^16");
 }
 
@@ -369,7 +368,7 @@ static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   generate_u16_range_check_cols(ctx, d_cols, N, 0, 24 * 16 - 3, lookups);
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   SBN_REQUIRE(h_err != 2, "G1 coordinate is not a canonical Fq residue");
   SBN_REQUIRE(!h_err, "degenerate G1 input: the chain hit the point at infinity or two points with equal x (the reference panics here)");
   if (h_results) for (size_t i = 0; i < n; i++) memcpy(h_results + i * 8, res.data() + i * 16, 64);
@@ -399,7 +398,7 @@ static void generate_exp_tail(sbn_ctx* ctx, const AirDesc& air, u64* d_cols, con
 static void check_chain_error(sbn_ctx* ctx, int* d_err, const char* what) {
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   SBN_REQUIRE(h_err != 2, "input coordinate is not a canonical Fq residue");
   SBN_REQUIRE(!h_err, what);
 }
@@ -637,7 +636,7 @@ static void generate_fq12(sbn_ctx* ctx, const AirDesc& air, const void* ios, boo
   DevBuf<unsigned char> buf; const void* d_ios = stage_ios<unsigned char>(ctx, ios, on_device, n * io_size, buf);
   if (u64v) {   // exp_val must be a canonical field element (it is a public input: exp_u64.rs:106)
     std::vector<unsigned char> h(n * io_size);
-    if (on_device) { CUDA_CHECK(cudaMemcpyAsync(h.data(), ios, h.size(), cudaMemcpyDeviceToHost, ctx->stream)); CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); }
+    if (on_device) { CUDA_CHECK(cudaMemcpyAsync(h.data(), ios, h.size(), cudaMemcpyDeviceToHost, ctx->stream)); ctx->sync(); }
     else memcpy(h.data(), ios, h.size());
     for (size_t i = 0; i < n; i++) { u64 e; memcpy(&e, h.data() + i * io_size + 768, 8); SBN_REQUIRE(e < GL_P, "Fq12ExpU64Stark: exp_val is not a canonical field element"); }
   }
@@ -668,7 +667,7 @@ static void generate_modular(sbn_ctx* ctx, const AirDesc& air, const void* ios, 
   generate_split_u16_range_check_cols(ctx, d_cols, N, 32, 111, 145);
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   SBN_REQUIRE(!h_err, "ModularStark input is not a canonical Fq residue");
 }
 
@@ -727,7 +726,7 @@ static void generate_gadget(sbn_ctx* ctx, const AirDesc& air, const void* ios, b
   }
   int h_err = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->sync();
   SBN_REQUIRE(h_err != 2, "gadget AIR input is not a canonical Fq residue");
   SBN_REQUIRE(h_err != 1, "G1Stark: the two points of a row have equal x (the addition gadget divides by b.x - a.x)");
 }

@@ -113,10 +113,9 @@ void compute_z_polys(sbn_ctx* ctx, const u64* trace, int logn, const PermInstanc
   int ntiles = (int)(N / ZT);
   size_t ne = perm.lhs.size();
   DevBuf<u32> d_lhs(ctx, ne), d_rhs(ctx, ne); DevBuf<u64> d_gamma(ctx, ne);
-  CUDA_CHECK(cudaMemcpyAsync(d_lhs, perm.lhs.data(), ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(d_rhs, perm.rhs.data(), ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(d_gamma, perm.gamma.data(), ne * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->upload(d_lhs, perm.lhs.data(), ne * 4);
+  ctx->upload(d_rhs, perm.rhs.data(), ne * 4);
+  ctx->upload(d_gamma, perm.gamma.data(), ne * 8);
   DevBuf<u64> tn(ctx, (size_t)nz * ntiles), td(ctx, (size_t)nz * ntiles);
   dim3 grid(ntiles, nz);
   KScope ks(ctx, "zpoly");

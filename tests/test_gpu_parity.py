@@ -381,3 +381,61 @@ def test_g1_256_instances_verifies(ctx, sbn, orc):
     assert ok, why
     t = bytearray(pb); t[len(t) // 2] ^= 2
     assert not orc.Air(orc.AIR_G1_EXP, n).verify(bytes(t))[0]
+
+
+def test_prove_batch_matches_single_proofs(ctx, sbn, golden):
+    """sbn_prove_batch: B independent proofs in one call, several in flight on the lanes of the batch.
+    Every element must be byte-identical to the proof sbn_prove returns for the same inputs (host inputs and device inputs, more
+    proofs than lanes, mixed AIR sizes across calls); the G1 element with the default seed must hit the committed golden."""
+    syn = sbn.synthetic
+    batch = sbn.Batch(0, lanes=3)
+    try:
+        for cls_name, gen, n, seeds in (("G1ExpStark", "g1_exp_ios", 128, (0x5EED0000, 11, 12, 13, 14)), ("FqExpStark", "fq_exp_ios", 128, (21, 22)),
+                                        ("Fq12ExpStark", "fq12_exp_ios", 2, (31, 32, 33, 34))):
+            stark = getattr(sbn, cls_name)(n, ctx)
+            cfg = stark.config()
+            raws = [getattr(syn, gen)(n, seed=s) for s in seeds]
+            singles = []
+            for raw in raws:
+                tr = stark.generate_trace(raw)
+                ios = syn.fill_outputs(raw, tr.results(), stark.io_size, stark.io_size - 8 * stark.result_words)
+                singles.append(sbn.prove(stark, cfg, tr, stark.generate_public_inputs(ios)).to_bytes())
+                tr.free()
+            got = [p.to_bytes() for p in sbn.prove_batch(stark, cfg, batch, raws)]
+            assert got == singles, cls_name
+            if cls_name == "G1ExpStark":
+                assert hashlib.sha256(got[0]).hexdigest() == golden["g1_128"]["proof_sha256"]
+                # device-resident inputs
+                import torch
+                dev = [torch.frombuffer(bytearray(r), dtype=torch.uint8).cuda() for r in raws[:2]]
+                torch.cuda.synchronize()
+                got_dev = [p.to_bytes() for p in sbn.prove_batch(stark, cfg, batch, [t.data_ptr() for t in dev], on_device=True)]
+                assert got_dev == singles[:2]
+                # caller-filled outputs (fill_outputs=False) give the same proof; a wrong output does not (public inputs differ)
+                tr = stark.generate_trace(raws[1])
+                filled = syn.fill_outputs(raws[1], tr.results(), stark.io_size, stark.io_size - 8 * stark.result_words)
+                tr.free()
+                assert sbn.prove_batch(stark, cfg, batch, [filled], fill_outputs=False)[0].to_bytes() == singles[1]
+        assert batch.launch_count > 0
+        # an invalid element fails the whole call with the library's message and returns nothing
+        stark = sbn.G1ExpStark(128, ctx)
+        bad = bytearray(syn.g1_exp_ios(128, seed=5)); bad[64:128] = bad[0:64]; bad[128] |= 1   # x == offset: division by zero in the first addition
+        with pytest.raises(sbn.SbnError):
+            sbn.prove_batch(stark, stark.config(), batch, [bytes(bad)])
+    finally:
+        batch.close()
+
+
+def test_context_destroy_with_live_trace_is_deferred(sbn):
+    """sbn_ctx_destroy while a trace is alive must not free the allocator under it (the trace's free comes later)."""
+    c = sbn.Context(0)
+    stark = sbn.ModularStark(512, c)
+    tr = stark.generate_trace(sbn.synthetic.modular_ios(512))
+    before = tr.download()
+    c.close()            # deferred: the trace still holds a buffer
+    assert (tr.download() == before).all()
+    tr.free()            # last handle: the context goes now
+    c2 = sbn.Context(0)  # a fresh context still works
+    tr2 = sbn.ModularStark(512, c2).generate_trace(sbn.synthetic.modular_ios(512))
+    assert (tr2.download() == before).all()
+    tr2.free(); c2.close()

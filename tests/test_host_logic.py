@@ -170,6 +170,59 @@ def test_product_poseidon_host_path_kat(emu):
     assert int(st[0]) == 0x3c18a9786cb0b359 and int(st[11]) == 0x1792b1c4342109d7
 
 
+def test_device_poseidon_mds_digit_model_matches_plain_layer():
+    """Integer model of the device MDS layer of csrc/poseidon.cuh (16-bit digits, dp2a sums, BIASED constant digits from
+    poseidon_rc_dig16.inc, the 10-instruction stitch with 32-bit wrap-around semantics) against sum_i circ[i] s[i+k] + rc:
+    the stitch must give the same residue for arbitrary 64-bit representatives, including the extreme digit sums."""
+    P = 2**64 - 2**32 + 1
+    M32 = 2**32 - 1
+    circ = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+    inc = open(os.path.join(ROOT, "starky-bn254_b200", "csrc", "poseidon_rc_dig16.inc")).read()
+    dig = [int(x) for x in re.findall(r"\b\d+\b", inc.split("SBN_POSEIDON_RC_DIG16_LIST")[1])]
+    assert len(dig) == 372 * 4
+    rc_txt = open(os.path.join(ROOT, "starky-bn254_b200", "csrc", "poseidon_rc.inc")).read()
+    rc = [int(x, 16) for x in re.findall(r"0x[0-9a-f]{16}", rc_txt)] + [0] * 12
+    for i in range(372):   # the biased digits represent the same constants and keep digit 0 above the largest fold term
+        d = dig[4 * i:4 * i + 4]
+        assert sum(x << (16 * k) for k, x in enumerate(d)) % P == rc[i] and d[0] >= 1024 and max(d) < 65536 + 1024
+
+    def stitch(c):
+        assert all(0 <= x < 2**25 for x in c)
+        rot = ((c[3] << 16) | (c[3] >> 16)) & M32
+        a = c[0] - (c[3] >> 16)
+        assert a >= 0
+        t1 = (c[1] << 16) & M32
+        b = (c[1] >> 16) + c[2]
+        s0 = a + t1
+        s1 = b + rot + (s0 >> 32)
+        e = (-(s1 >> 32)) & M32
+        r0 = (s0 & M32) + e
+        r1 = (s1 & M32) + (r0 >> 32)
+        assert r1 < 2**32
+        return (r1 << 32) | (r0 & M32)
+
+    def layer(s, off):
+        out = []
+        for r in range(12):
+            c = list(dig[4 * (off + r):4 * (off + r) + 4])
+            for l in range(12):
+                coef = circ[(l - r) % 12] + (8 if l == 0 and r == 0 else 0)
+                for d in range(4):
+                    c[d] += ((s[l] >> (16 * d)) & 0xFFFF) * coef
+            out.append(stitch(c))
+        return out
+
+    rng = random.Random(11)
+    cases = [[rng.getrandbits(64) for _ in range(12)] for _ in range(300)]
+    cases += [[2**64 - 1] * 12, [0] * 12, [P - 1] * 12, [0xFFFF_0000_FFFF_FFFF] * 12, [0xFFFF_FFFF_0000_0000] * 12]
+    cases += [[rng.choice([0, 2**64 - 1, 0xFFFF, 0xFFFF << 48, P]) for _ in range(12)] for _ in range(300)]
+    for s in cases:
+        for off in (12, 60, 360):
+            want = [(sum(circ[i] * s[(i + k) % 12] for i in range(12)) + (8 * s[0] if k == 0 else 0) + rc[off + k]) % P for k in range(12)]
+            got = layer(s, off)
+            assert [g % P for g in got] == want and all(g < 2**64 for g in got)
+
+
 def _w8(v):
     return np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
 

@@ -1,5 +1,12 @@
 // Micro-benchmark of the leaf-hash kernel variants (not product code): synthetic LDE, 2^17 leaves.
+// -DPOSEIDON_R01: the frozen round-1 permutation (poseidon_r01_baseline.cuh) for before / after numbers on the same box.
+#ifdef POSEIDON_R01
+#include "poseidon_r01_baseline.cuh"
+#define VARIANT "r01-baseline"
+#else
 #include "../../starky-bn254_b200/csrc/poseidon.cuh"
+#define VARIANT "current"
+#endif
 #include <cstdio>
 #include <vector>
 
@@ -48,7 +55,7 @@ int main(int argc, char** argv) {
   float ms;
 #define RUN(BS, MINB) ms = run<BS, MINB>(lde, L, ncols, dig, 3); cudaMemcpy(h.data(), dig + 4 * 777, 32, cudaMemcpyDeviceToHost); \
   printf("%s bs=%d minb=%d  %.3f ms  %.1f Mperm/s  dig=%016llx\n", VARIANT, BS, MINB, ms, perms / ms / 1e3, h[0]);
-  RUN(128, 1) RUN(128, 6) RUN(128, 7) RUN(128, 8) RUN(128, 9) RUN(128, 10) RUN(64, 14) RUN(64, 16) RUN(256, 3) RUN(256, 4) RUN(32, 28) RUN(32, 32)
+  RUN(128, 1) RUN(128, 6) RUN(128, 8) RUN(64, 14) RUN(256, 3)
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
   return 0;

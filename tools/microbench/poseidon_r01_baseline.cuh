@@ -12,10 +12,10 @@
 // proof), byte digits on IDP.4A (48.4 ms), O(t) partial rounds with full 64-bit constants (58.8 ms), unrolled loop shapes.
 // Host path (Fiat-Shamir challenger): branch-free arithmetic, partial rounds in the O(t) form (poseidon_fast.inc).
 #pragma once
-#include "gl.cuh"
+#include "../../starky-bn254_b200/csrc/gl.cuh"
 
 static const u64 h_poseidon_rc[360] = {
-#include "poseidon_rc.inc"
+#include "../../starky-bn254_b200/csrc/poseidon_rc.inc"
     SBN_POSEIDON_RC_LIST};
 #ifdef __CUDACC__
 static __constant__ u64 d_poseidon_rc[372] = {SBN_POSEIDON_RC_LIST, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // + a zero "round 30"
@@ -23,7 +23,7 @@ static __constant__ u64 d_poseidon_rc[372] = {SBN_POSEIDON_RC_LIST, 0, 0, 0, 0, 
 
 #ifdef __CUDACC__
 static __constant__ __align__(16) u32 d_poseidon_rc_dig16[372 * 4] = {
-#include "poseidon_rc_dig16.inc"
+#include "poseidon_rc_dig16_r01.inc"
     SBN_POSEIDON_RC_DIG16_LIST};
 #endif
 #ifdef __CUDA_ARCH__
@@ -46,18 +46,11 @@ __device__ __forceinline__ u64 poseidon_sbox_nc(u64 x) {
 __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) { u32 r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
 // MDS layer on 16-bit digits with the 2-way dot product (IDP.2A: two 16-bit values times two bytes): each lane is cut into four
 // digits, the digits of two lanes share a word (one PRMT), 12 lanes x 4 digits x 6 lane pairs = 288 dot products where the limb
-// form needed 435 multiply-adds on the same pipe.  A digit sum is < 65535 * 264 + 65535 + 1024 < 2^25; the four sums c0..c3 are
-// stitched at 16-bit spacing into 74 bits and folded with 2^64 = 2^32 - 1:
-//   value = (c0 - h) + c1 2^16 + (c2 + h) 2^32 + (c3 mod 2^16) 2^48,  h = c3 >> 16 <= 264.
-// The round constants enter as the initial accumulators, BIASED (tools/gen_poseidon_constants.py): digits of (rc - 1024) mod p
-// with 1024 added back to digit 0, so c0 >= 1024 > h and the value above is a sum of non-negative terms that wraps 2^64 at most
-// once; the wrap is folded by adding 2^32 - 1, which cannot wrap again (the high word is < 2^27 after a wrap).
-// Instruction placement (ptxas lowers plain add / sub / shl / mov to IMAD.* on the multiplier pipe, which is this kernel's
-// binding pipe): c0 - h is one signed dp2a against c3's own halves (replaces a PRMT + an IMAD.IADD), the 16-bit
-// shifts are PRMTs, (c3 mod 2^16) 2^16 + h is one PRMT (rotation by 16), and every add of the stitch is part of a carry chain.
+// form needed 435 multiply-adds on the same pipe.  A digit sum is < 65535 * 292 + 65535 < 2^25; the four sums are stitched at
+// 16-bit spacing into 74 bits and folded with 2^64 = 2^32 - 1 on the ALU pipe.
 __device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b, u32 c) { u32 r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ u32 dp2a_hi(u32 a, u32 b, u32 c) { u32 r; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-__device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], const uint4* __restrict__ rc /* this layer's 12 biased digit quads */) {
+__device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], int rc_off) {
   u32 A[4][6];   // A[d][j] = 16-bit digit d of lanes 2j (low half) and 2j+1 (high half)
 #pragma unroll
   for (int j = 0; j < 6; j++) {
@@ -67,7 +60,7 @@ __device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], const uint4* __rest
   }
 #pragma unroll
   for (int r = 0; r < 12; r++) {
-    const uint4 k = rc[r];
+    const uint4 k = reinterpret_cast<const uint4*>(d_poseidon_rc_dig16)[rc_off + r];
     u32 c[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
     for (int q = 0; q < 3; q++) {
@@ -77,18 +70,21 @@ __device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], const uint4* __rest
     }
     u32 r0, r1;
     asm("{\n\t"
-        ".reg .u32 rot, a, b, t1, t, e;\n\t"
-        "prmt.b32 rot, %5, %5, 0x1032;\n\t"        // (c3 << 16) | (c3 >> 16) = (c3 mod 2^16) 2^16 + h
-        "dp2a.lo.u32.s32 a, %5, 0xFF00, %2;\n\t"    // c0 + 0 * (c3 mod 2^16) - 1 * (c3 >> 16) = c0 - h
-        "prmt.b32 t1, %3, 0, 0x1044;\n\t"          // c1 << 16
-        "shf.r.clamp.b32 b, %3, 0, 16;\n\t"         // c1 >> 16
-        "add.u32 b, b, %4;\n\t"
-        "add.cc.u32 %0, a, t1;\n\t"
-        "addc.cc.u32 %1, b, rot;\n\t"
-        "addc.u32 t, 0x7FFFFFFF, 0;\n\t"            // bit 31 = carry (never mix add.cc with subc: ptxas keeps the carry as NOT borrow)
-        "prmt.b32 e, t, 0, 0xBBBB;\n\t"             // sign of byte 3 replicated: 0xFFFFFFFF (= 2^32 - 1 as a 64-bit addend) after a wrap
+        ".reg .u32 t1, t2, t3, t4, h, b, d, e, f;\n\t"
+        "shl.b32 t1, %3, 16;\n\t" "shr.u32 t2, %3, 16;\n\t" "add.u32 t3, t2, %4;\n\t"
+        "shl.b32 t4, %5, 16;\n\t" "shr.u32 h, %5, 16;\n\t"
+        "add.cc.u32 %0, %2, t1;\n\t"
+        "addc.cc.u32 %1, t3, t4;\n\t"
+        "addc.u32 h, h, 0;\n\t"              // value = h 2^64 + (%1:%0), h < 2^10
+        "sub.cc.u32 %0, %0, h;\n\t"          // + h (2^32 - 1)
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 b, 0, 0;\n\t"
+        "add.cc.u32 %1, %1, h;\n\t"
+        "addc.u32 d, b, 0;\n\t"              // net 64-bit wraps, in {-1, 0, 1}
+        "neg.s32 e, d;\n\t"
+        "shr.s32 f, d, 31;\n\t"
         "add.cc.u32 %0, %0, e;\n\t"
-        "addc.u32 %1, %1, 0;\n\t"
+        "addc.u32 %1, %1, f;\n\t"
         "}"
         : "=&r"(r0), "=&r"(r1)
         : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
@@ -129,7 +125,7 @@ HD void poseidon_mds(u64 s[12]) {
 // 128-bit accumulators for the MDS layer; the 22 partial rounds run in the O(t)-per-round form whose constants
 // tools/gen_poseidon_fast.py derives and checks against the plain permutation (poseidon_fast.inc).
 static const u64 h_poseidon_fast[639] = {
-#include "poseidon_fast.inc"
+#include "../../starky-bn254_b200/csrc/poseidon_fast.inc"
     SBN_POSEIDON_FAST_LIST};
 // Branch-free arithmetic on arbitrary 64-bit representatives (carry / borrow of random operands is unpredictable, a
 // mispredicted branch costs more than the whole reduction); only the permutation's outputs are canonicalised.
@@ -191,31 +187,18 @@ static inline void poseidon_permute_host(u64 s[12]) {
 // Canonical in, canonical out.
 HD void poseidon_permute(u64 s[12]) {
 #ifdef __CUDA_ARCH__
-  // Two loop bodies -- a full round (12 S-boxes + MDS) and a partial round (1 S-box + MDS) -- so that each is scheduled for its
-  // own instruction mix, both small enough to stay in the instruction cache (a fully unrolled permutation, > 90 KB, stalls on
-  // instruction fetch; one rolled body with a uniform `full` branch was the round-1 shape).
+  // One rolled round loop (uniform `full` branch) keeps the hot body small enough to stay in the instruction cache; a fully
+  // unrolled permutation (> 90 KB) stalls on instruction fetch.
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_nc(s[i], d_poseidon_rc[i]);
-  // The constant-bank index is kept in a per-thread (vector) register: inputs are canonical (< p), so `zero` is always 0, but not
-  // provably so.  With a uniform index ptxas re-materialises it for every one of the 24 constant loads of a layer (24 IMAD.U32
-  // per layer on the multiplier pipe); off a vector register they are one base + immediates.
-  const u32 zero = s[11] == ~0ULL ? 1u : 0u;
-  const uint4* rc = reinterpret_cast<const uint4*>(d_poseidon_rc_dig16) + 12 + zero;
 #pragma unroll 1
-  for (int half = 0; half < 2; half++) {
-#pragma unroll 1
-    for (int k = 0; k < 4; k++, rc += 12) {
+  for (int r = 0; r < 30; r++) {
+    s[0] = poseidon_sbox_nc(s[0]);
+    if (r < 4 || r >= 26) {
 #pragma unroll
-      for (int i = 0; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
-      poseidon_mds_dp2a(s, rc);
+      for (int i = 1; i < 12; i++) s[i] = poseidon_sbox_nc(s[i]);
     }
-    if (half == 0) {
-#pragma unroll 1
-      for (int k = 0; k < 22; k++, rc += 12) {
-        s[0] = poseidon_sbox_nc(s[0]);
-        poseidon_mds_dp2a(s, rc);
-      }
-    }
+    poseidon_mds_dp2a(s, 12 * (r + 1));
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);

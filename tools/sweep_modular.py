@@ -28,9 +28,18 @@ def fast_ios(n, seed=5):
     return w.tobytes()
 
 
+def main_from_bench(args):
+    """`python bench.py --sweep modular`: the same sweep, 2^16 .. 2^22 rows (SBN_SWEEP_MAX_LOG / SBN_SWEEP_MIN_LOG override)."""
+    return run(int(os.environ.get("SBN_SWEEP_MAX_LOG", "22")), int(os.environ.get("SBN_SWEEP_MIN_LOG", "16")))
+
+
 def main():
     max_log = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     min_log = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    return run(max_log, min_log)
+
+
+def run(max_log, min_log):
     sbn = entry.load_package()
     ctx = sbn.Context(0)
     peaks = {}
