@@ -289,7 +289,7 @@ u64 fri_pow_search(sbn_ctx* ctx, const u64 state[12], int pos, int pow_bits) {
 //   for each FRI layer j:      evals[2 * arity_j], path[proof_len_j * 4]
 struct GatherDesc {
   int noracles, nlayers, logn, rate_bits;
-  const u64* lde[4]; int ncols[4]; const u64* odig[4]; int oplen[4]; size_t olevel_off[4][32];
+  const u64* lde[4]; int ncols[4]; int sub_coset[4]; const u64* odig[4]; int oplen[4]; size_t olevel_off[4][32];
   const u64* lleaves[8]; int larity_bits[8]; const u64* ldig[8]; int lplen[8]; size_t llevel_off[8][32];
 };
 __global__ void __launch_bounds__(256) k_gather_queries(GatherDesc d, const u64* __restrict__ indices, size_t record_words, u64* __restrict__ out) {
@@ -301,8 +301,12 @@ __global__ void __launch_bounds__(256) k_gather_queries(GatherDesc d, const u64*
   for (int o = 0; o < d.noracles; o++) {
     // leaf x_index holds the LDE row of natural index bitrev(x_index): coset b = i mod 2^r, k = i >> r
     size_t i = bitrev32((u32)x_index0, logL);
-    size_t src = (i & ((size_t(1) << d.rate_bits) - 1)) * N + (i >> d.rate_bits);
-    for (int c = threadIdx.x; c < d.ncols[o]; c += blockDim.x) rec[w + c] = d.lde[o][(size_t)c * L + src];
+    const size_t b = i & ((size_t(1) << d.rate_bits) - 1), k = i >> d.rate_bits;
+    if (d.sub_coset[o] < 0) {
+      for (int c = threadIdx.x; c < d.ncols[o]; c += blockDim.x) rec[w + c] = d.lde[o][(size_t)c * L + b * N + k];
+    } else if (d.lde[o] && (size_t)d.sub_coset[o] == b) {
+      for (int c = threadIdx.x; c < d.ncols[o]; c += blockDim.x) rec[w + c] = d.lde[o][(size_t)c * N + k];
+    }
     w += d.ncols[o];
     for (int t = threadIdx.x; t < d.oplen[o] * 4; t += blockDim.x) {
       int lvl = t >> 2;
@@ -339,7 +343,7 @@ void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, i
   GatherDesc d; memset(&d, 0, sizeof d);
   d.noracles = (int)oracles.size(); d.nlayers = (int)layers.size(); d.logn = logn; d.rate_bits = rate_bits;
   for (size_t o = 0; o < oracles.size(); o++) {
-    d.lde[o] = oracles[o].lde; d.ncols[o] = oracles[o].ncols; d.odig[o] = oracles[o].tree->digests; d.oplen[o] = oracles[o].tree->proof_len();
+    d.lde[o] = oracles[o].lde; d.ncols[o] = oracles[o].ncols; d.sub_coset[o] = oracles[o].sub_coset; d.odig[o] = oracles[o].tree->digests; d.oplen[o] = oracles[o].tree->proof_len();
     for (int l = 0; l < oracles[o].tree->num_levels(); l++) d.olevel_off[o][l] = oracles[o].tree->level_off[l];
   }
   for (size_t j = 0; j < layers.size(); j++) {

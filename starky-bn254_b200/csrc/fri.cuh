@@ -29,7 +29,10 @@ void fri_fold_coeffs(sbn_ctx* ctx, const u64* d_coeffs, size_t n, int arity_bits
 // smallest w with leading_zeros(poseidon(state with state[pos] = w)[7]) >= pow_bits
 u64 fri_pow_search(sbn_ctx* ctx, const u64 state[12], int pos, int pow_bits);
 
-struct QueryOracle { const u64* lde; int ncols; const DevMerkleTree* tree; };
+// sub_coset < 0: `lde` is the whole batch [col][b][k].  sub_coset = b (streamed commitment): `lde` holds sub-coset b only
+// ([col][k], column stride N); the rows of queries that fall into another sub-coset are left untouched in the record, so the
+// caller gathers into the same device records once per sub-coset.  lde == nullptr: paths only.
+struct QueryOracle { const u64* lde; int ncols; const DevMerkleTree* tree; int sub_coset = -1; };
 // Gathers all query openings into one flat u64 record per query (layout documented in fri.cu).
 size_t fri_query_record_words(const std::vector<QueryOracle>& oracles, const std::vector<FriLayer*>& layers);
 void fri_gather_queries(sbn_ctx* ctx, const std::vector<QueryOracle>& oracles, int logn, int rate_bits, const std::vector<FriLayer*>& layers,

@@ -9,12 +9,14 @@
 #include "merkle.cuh"
 #include "poseidon.cuh"
 
+// sub_coset < 0: the whole batch lde[col][b][k] (col_stride = L); sub_coset = b: one sub-coset sub[col][k] (col_stride = N) of a
+// streamed commitment -- the digests land at the same positions either way.
 __global__ void __launch_bounds__(128) k_leaf_hash(const u64* __restrict__ lde, size_t col_stride, int ncols, int logn, int rate_bits,
-                                                   u64* __restrict__ digests) {
-  const size_t L = size_t(1) << (logn + rate_bits);
+                                                   u64* __restrict__ digests, int sub_coset) {
+  const size_t L = size_t(1) << (logn + (sub_coset < 0 ? rate_bits : 0));
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= L) return;
-  const u32 b = (u32)(idx >> logn), k = (u32)(idx & ((size_t(1) << logn) - 1));
+  const u32 b = sub_coset < 0 ? (u32)(idx >> logn) : (u32)sub_coset, k = (u32)(idx & ((size_t(1) << logn) - 1));
   const size_t pos = ((size_t)bitrev32(b, rate_bits) << logn) + bitrev32(k, logn);
   u64 st[12];
 #pragma unroll
@@ -79,7 +81,13 @@ void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t) {
 void merkle_leaf_hash_only(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int rate_bits, DevMerkleTree* t) {
   size_t L = size_t(1) << (logn + rate_bits);
   KScope ks(ctx, "merkle_leaf_hash");
-  k_leaf_hash<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(lde, L, ncols, logn, rate_bits, t->digests);
+  k_leaf_hash<<<(unsigned)((L + 127) / 128), 128, 0, ctx->stream>>>(lde, L, ncols, logn, rate_bits, t->digests, -1);
+  LAUNCH_CHECK(ctx);
+}
+void merkle_leaf_hash_sub_coset(sbn_ctx* ctx, const u64* sub, int ncols, int logn, int rate_bits, int b, DevMerkleTree* t) {
+  size_t N = size_t(1) << logn;
+  KScope ks(ctx, "merkle_leaf_hash");
+  k_leaf_hash<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(sub, N, ncols, logn, rate_bits, t->digests, b);
   LAUNCH_CHECK(ctx);
 }
 

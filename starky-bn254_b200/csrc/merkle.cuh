@@ -19,5 +19,8 @@ void merkle_commit_lde(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int ra
 // Build the upper levels from already-written leaf digests (tree->digests level 0) and fetch the cap.
 void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t);
 void merkle_alloc(sbn_ctx* ctx, DevMerkleTree* t, size_t nleaves, int cap_height);
+// Leaf digests of ONE sub-coset b (values sub[col][k], column stride N) of a streamed commitment: the LDE is produced, hashed
+// and dropped one sub-coset at a time (config 5 at 2^22 rows does not fit otherwise); same digest positions as the full batch.
+void merkle_leaf_hash_sub_coset(sbn_ctx* ctx, const u64* sub, int ncols, int logn, int rate_bits, int b, DevMerkleTree* t);
 // Leaf digests only (level 0 of an already allocated tree); used by the commitment micro-benchmark.
 void merkle_leaf_hash_only(sbn_ctx* ctx, const u64* lde, int ncols, int logn, int rate_bits, DevMerkleTree* t);

@@ -302,14 +302,14 @@ template <int L> static void launch_pass2(sbn_ctx* ctx, dim3 grid, size_t smem, 
 #define NTT_DISPATCH_L(l, CALL) \
   switch (l) { case 6: { constexpr int L = 6; CALL; } break; case 7: { constexpr int L = 7; CALL; } break; case 8: { constexpr int L = 8; CALL; } break; \
     case 9: { constexpr int L = 9; CALL; } break; case 10: { constexpr int L = 10; CALL; } break; case 11: { constexpr int L = 11; CALL; } break; \
-    case 12: { constexpr int L = 12; CALL; } break; default: SBN_REQUIRE(false, "ntt: unsupported sub-transform size"); }
+    case 12: { constexpr int L = 12; CALL; } break; case 13: { constexpr int L = 13; CALL; } break; default: SBN_REQUIRE(false, "ntt: unsupported sub-transform size"); }
 
 // Transform of `ncols` columns.  pre_base c != 0: evaluate on the coset c<w> (input times c^n); postscale: optional table
 // the output is multiplied by (output index k); inverse: w^-1 and 1/N.
 void ntt_batch(sbn_ctx* ctx, const u64* in, size_t in_stride, u64* out, size_t out_stride, int ncols, int logn, bool inverse,
                u64 pre_base, const u64* postscale) {
   if (ncols <= 0) return;
-  SBN_REQUIRE(logn >= 1 && logn <= 24, "ntt: unsupported size");
+  SBN_REQUIRE(logn >= 1 && logn <= 26, "ntt: unsupported size");
   if (pre_base == 1) pre_base = 0;
   const NttTables tb = get_ntt_tables(ctx, logn);
   const u64* W = inverse ? tb.w_inv : tb.w_fwd;
@@ -370,6 +370,13 @@ void lde_columns(sbn_ctx* ctx, const u64* coeffs, u64* lde, int ncols, int logn,
     u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, b));
     ntt_batch(ctx, coeffs, N, lde + (size_t)b * N, N * R, ncols, logn, false, sb, nullptr);
   }
+}
+
+// One sub-coset b of the LDE: out[col][k] = value at natural LDE index k 2^r + b (column stride N).
+void lde_sub_coset(sbn_ctx* ctx, const u64* coeffs, u64* out, int ncols, int logn, int rate_bits, int b) {
+  size_t N = size_t(1) << logn;
+  const u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(gl_root_of_unity(logn + rate_bits), (u64)b));
+  ntt_batch(ctx, coeffs, N, out, N, ncols, logn, false, sb, nullptr);
 }
 
 // ---- one LDE class (intra-proof sharding) ----

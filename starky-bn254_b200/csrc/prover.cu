@@ -85,7 +85,30 @@ struct Shard {
 struct Commitment {
   DevBuf<u64> coeffs, lde, lde_next; DevMerkleTree tree; int ncols = 0;
   std::vector<u64> cap;   // the full cap (2^cap_height x 4), identical on every rank
+  bool streamed = false;  // the LDE was hashed sub-coset by sub-coset and dropped: `lde` is empty, sub-cosets are recomputed on demand
 };
+// Streamed commitment (config 5 at 2^22 rows: trace + coefficients + LDE of 812 + 444 columns do not fit 180 GB): every sub-coset
+// b of the LDE is evaluated into `scratch` ([ncols][N]), its N leaves are hashed, and the values are dropped; the tree (all digest
+// levels) is kept.  The footprint is independent of rate_bits; the same cap, leaf for leaf, as commit_from_coeffs.
+static void commit_streamed(sbn_ctx* ctx, Commitment& c, int ncols, int logn, int rate_bits, int cap_height, u64* scratch) {
+  c.ncols = ncols; c.streamed = true;
+  merkle_alloc(ctx, &c.tree, (size_t(1) << logn) << rate_bits, cap_height);
+  for (int b = 0; b < (1 << rate_bits); b++) {
+    lde_sub_coset(ctx, c.coeffs, scratch, ncols, logn, rate_bits, b);
+    merkle_leaf_hash_sub_coset(ctx, scratch, ncols, logn, rate_bits, b, &c.tree);
+  }
+  merkle_build_from_leaf_digests(ctx, &c.tree);
+  c.cap = c.tree.cap;
+}
+// Streaming is chosen when the resident footprint of the plain prover (coefficients + LDE of the trace and Z batches + Z values,
+// beside the trace the caller holds) would not fit the device; SBN_STREAMING=0/1 forces the choice (tests: byte-identical proofs).
+static bool want_streaming(size_t C, size_t Z, size_t N, int rate_bits) {
+  if (const char* e = getenv("SBN_STREAMING")) return atoi(e) != 0;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  const double need = 8.0 * (double)N * ((double)(C + Z) * (1.0 + (double)(1 << rate_bits)) + (double)Z) * 1.1;
+  return need > 0.8 * (double)total_b - 8.0 * (double)N * (double)C;
+}
 static void commit_from_coeffs(sbn_ctx* ctx, const Shard& sh, Commitment& c, int ncols, int logn, int rate_bits, int cap_height, bool need_next) {
   size_t N = size_t(1) << logn;
   c.ncols = ncols;
@@ -173,6 +196,15 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
 
   // ---- trace commitment ----
   Commitment trace_c;
+  const size_t nz_cols = air.perm_pairs.empty() ? 0 : (air.perm_pairs.size() * nch + air.quotient_degree_factor() - 1) / air.quotient_degree_factor();
+  const bool streaming = !sh.on() && want_streaming(air.num_columns, nz_cols, N, rate_bits);
+  DevBuf<u64> scratch_t, scratch_z;   // one sub-coset of the trace / Z batch (streaming only)
+  if (streaming) {
+    trace_c.coeffs = DevBuf<u64>(ctx, air.num_columns * N);
+    intt_columns(ctx, tr->cols, trace_c.coeffs, (int)air.num_columns, logn);
+    scratch_t = DevBuf<u64>(ctx, air.num_columns * N);
+    commit_streamed(ctx, trace_c, (int)air.num_columns, logn, rate_bits, cap_height, scratch_t);
+  } else
   commit_from_values(ctx, sh, trace_c, tr->cols, (int)air.num_columns, logn, rate_bits, cap_height, true);
   tm.mark("compute trace commitment");
   Challenger ch;
@@ -208,6 +240,13 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
       CUDA_CHECK(cudaMemcpyAsync(proof->dbg_z.data(), zvals, nz * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
       ctx->sync();
     }
+    if (streaming) {
+      z_c.coeffs = DevBuf<u64>(ctx, nz * N);
+      intt_columns(ctx, zvals, z_c.coeffs, (int)nz, logn);
+      zvals.reset();                          // its block is reused for the sub-coset scratch
+      scratch_z = DevBuf<u64>(ctx, nz * N);
+      commit_streamed(ctx, z_c, (int)nz, logn, rate_bits, cap_height, scratch_z);
+    } else
     commit_from_values(ctx, sh, z_c, zvals, (int)nz, logn, rate_bits, cap_height, true);
     tm.mark("compute permutation Z commitments");
     ch.observe_n(z_c.cap.data(), z_c.cap.size());
@@ -224,7 +263,22 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   Commitment q_c;
   const int nq_polys = qdf * nch;
   q_c.coeffs = DevBuf<u64>(ctx, (size_t)nq_polys * N);
-  if (!sh.on()) {
+  if (streaming) {
+    // the two half-cosets of the quotient coset one after the other, each evaluated from the coefficients into the scratch
+    // buffers (exactly the classes a world-2 sharded proof gives its two ranks)
+    const size_t Mp = N;
+    DevBuf<u64> acc_local(ctx, (size_t)SBN_MAX_CHALLENGES * Mp), acc_full(ctx, (size_t)nch * 2 * N);
+    for (u32 bq = 0; bq < 2; bq++) {
+      QDomain dom; dom.m = 1; dom.sigma = bq;
+      lde_class(ctx, trace_c.coeffs, scratch_t, trace_c.ncols, logn, 1, 1, bq);
+      dom.trace = dom.trace_next = scratch_t;
+      if (uses_perm) { lde_class(ctx, z_c.coeffs, scratch_z, z_c.ncols, logn, 1, 1, bq); dom.zs = dom.zs_next = scratch_z; }
+      quotient_eval(ctx, air, dom, nullptr, nullptr, perm, d_pis, alphas, nch, logn, rate_bits, acc_local);
+      for (int c = 0; c < nch; c++)
+        CUDA_CHECK(cudaMemcpyAsync(acc_full + ((size_t)c * 2 + bq) * N, acc_local + (size_t)c * Mp, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    quotient_finish(ctx, acc_full, nch, logn, q_c.coeffs);
+  } else if (!sh.on()) {
     compute_quotient_chunks(ctx, air, trace_c.lde, uses_perm ? z_c.lde.get() : nullptr, perm, d_pis, alphas, nch, logn, rate_bits, q_c.coeffs);
   } else {
     // this rank's class of the quotient coset (rate_bits = 1: the quotient coset is the LDE coset), then all classes -> [chal][bq][k]
@@ -388,7 +442,22 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   std::vector<FriLayer*> lp; for (auto& l : layers) lp.push_back(&l);
   const size_t rw_o = fri_query_record_words(qo, {}), rw_l = fri_query_record_words({}, lp), nq = indices.size();
   std::vector<u64> rec_o(rw_o * nq), rec_l(rw_l * nq);
-  if (!sh.on()) {
+  if (streaming) {
+    // rows of a streamed commitment: every sub-coset that holds a queried leaf is evaluated again and its rows are gathered
+    DevBuf<u64> d_rec(ctx, rw_o * nq);
+    const u64 rmask = (u64(1) << rate_bits) - 1;
+    for (int b = 0; b < (1 << rate_bits); b++) {
+      bool any = false;
+      for (u64 x : indices) any = any || ((u64)bitrev32((u32)x, logL) & rmask) == (u64)b;
+      if (!any) continue;
+      lde_sub_coset(ctx, trace_c.coeffs, scratch_t, C, logn, rate_bits, b);
+      if (Z) lde_sub_coset(ctx, z_c.coeffs, scratch_z, Z, logn, rate_bits, b);
+      std::vector<QueryOracle> qs; qs.push_back({scratch_t, C, &trace_c.tree, b}); if (Z) qs.push_back({scratch_z, Z, &z_c.tree, b}); qs.push_back({q_c.lde, nq_polys, &q_c.tree});
+      fri_gather_queries(ctx, qs, logn, rate_bits, {}, indices, nullptr, d_rec);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(rec_o.data(), d_rec, rec_o.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+  } else if (!sh.on()) {
     fri_gather_queries(ctx, qo, logn, rate_bits, {}, indices, rec_o.data());
   } else {
     // the rank that owns a leaf opens it: rows and paths live in its class batches, at the leaf's index inside the class
@@ -468,7 +537,6 @@ static void ctx_delete(sbn_ctx* ctx) {
   ctx->release_all();
   ctx->kresolve();
   for (auto e : ctx->kpool) cudaEventDestroy(e);
-  if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;   // the table set goes with its last owner

@@ -390,7 +390,7 @@ def test_prove_batch_matches_single_proofs(ctx, sbn, golden):
     syn = sbn.synthetic
     batch = sbn.Batch(0, lanes=3)
     try:
-        for cls_name, gen, n, seeds in (("G1ExpStark", "g1_exp_ios", 128, (0x5EED0000, 11, 12, 13, 14)), ("FqExpStark", "fq_exp_ios", 128, (21, 22)),
+        for cls_name, gen, n, seeds in (("G1ExpStark", "g1_exp_ios", 128, (0x5EED0001, 11, 12, 13, 14)), ("FqExpStark", "fq_exp_ios", 128, (21, 22)),
                                         ("Fq12ExpStark", "fq12_exp_ios", 2, (31, 32, 33, 34))):
             stark = getattr(sbn, cls_name)(n, ctx)
             cfg = stark.config()
@@ -439,3 +439,53 @@ def test_context_destroy_with_live_trace_is_deferred(sbn):
     tr2 = sbn.ModularStark(512, c2).generate_trace(sbn.synthetic.modular_ios(512))
     assert (tr2.download() == before).all()
     tr2.free(); c2.close()
+
+
+@pytest.mark.parametrize("case", ["modular_r1", "modular_r3", "g1"])
+def test_streaming_prover_is_byte_identical(ctx, sbn, golden, monkeypatch, case):
+    """The streamed prover (LDE hashed sub-coset by sub-coset and dropped, quotient per half-coset from the coefficients, opened
+    rows re-evaluated: what config 5 at 2^22 rows needs to fit one GPU) must return the same bytes as the resident one."""
+    if case == "g1":
+        stark = sbn.G1ExpStark(128, ctx)
+        raw = sbn.synthetic.g1_exp_ios(128)
+        cfg = stark.config()
+    else:
+        stark = sbn.ModularStark(4096, ctx)
+        raw = sbn.synthetic.modular_ios(4096)
+        cfg = stark.config()
+        cfg.rate_bits = 3 if case == "modular_r3" else 1
+    proofs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SBN_STREAMING", mode)
+        tr = stark.generate_trace(raw)
+        ios = sbn.synthetic.fill_outputs(raw, tr.results(), stark.io_size, stark.io_size - 8 * stark.result_words) if stark.result_words else raw
+        pi = stark.generate_public_inputs(ios) if stark.num_public_inputs else np.zeros(0, dtype=np.uint64)
+        proofs.append(sbn.prove(stark, cfg, tr, pi).to_bytes())
+        tr.free()
+    assert proofs[0] == proofs[1]
+    if case == "g1":
+        assert hashlib.sha256(proofs[1]).hexdigest() == golden["g1_128"]["proof_sha256"]
+
+
+def test_ntt_size_2_25(ctx):
+    """Sub-transform size 2^13 (2^25 = 2^12 x 2^13: the FRI codeword of config 5 at 2^22 rows and rate 8).  Size-independent checks:
+    the transform of -v is the negation of the transform of v, and a constant column interpolates to the constant polynomial."""
+    logn = 25
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    v = rng.integers(0, P, size=(1, n), dtype=np.uint64)
+    neg = np.where(v == 0, np.uint64(0), np.uint64(P) - v)
+    cf, lde, _ = ctx.commit_columns(v, 1, 4)
+    cf2, lde2, _ = ctx.commit_columns(neg, 1, 4)
+    assert (np.where(cf == 0, np.uint64(0), np.uint64(P) - cf) == cf2).all()
+    assert (np.where(lde == 0, np.uint64(0), np.uint64(P) - lde) == lde2).all()
+    # f(x) = c0 + c1 x evaluated on the coset 7 <w_2N>: lde[i] = c0 + c1 * 7 * w^i
+    lin = np.zeros((1, n), dtype=np.uint64)
+    w_n = pow(1753635133440165772, 1 << (32 - logn), P)
+    c0, c1 = 123456789, 987654321
+    # values of c0 + c1 x on the subgroup <w_N> at a few indices only would not define the column; use the coefficient route instead:
+    # a column equal to the constant c0 has coefficients (c0, 0, 0, ...) and a constant LDE
+    lin[:] = c0
+    cfl, ldel, _ = ctx.commit_columns(lin, 1, 4)
+    assert int(cfl[0][0]) == c0 and not cfl[0][1:].any() and (ldel == c0).all()
+    assert w_n and c1

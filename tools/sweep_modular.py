@@ -4,6 +4,7 @@ row count a parameter) at 2^16 .. 2^max rows, rate_bits 1..3: per-phase device m
 Merkle (K2 + K3: trace, Z and quotient commitments), Z polynomials (K4), quotient (K5) and the rest (K6), plus the achieved
 fraction of the HBM roofline for the NTT/LDE kernels.  Writes one JSON object per (rows, rate) to stdout.
     python tools/sweep_modular.py [max_log_rows=20] [min_log_rows=16]"""
+import hashlib
 import json
 import os
 import sys
@@ -54,26 +55,28 @@ def run(max_log, min_log):
         stark = sbn.ModularStark(n, ctx)
         for rate_bits in (1, 2, 3):
             L = n << rate_bits
-            need = 8 * ((C + PAIRS + Q) * (2 * n + L) + 2 * n * 24) * 1.15
-            if need > 150e9:
-                print(json.dumps({"rows_log2": logn, "rate_bits": rate_bits, "skipped": "needs %.0f GB of HBM (coset-sharding across GPUs or a streaming LDE: DESIGN.md §8)" % (need / 1e9)}))
-                continue
             cfg = stark.config()
             cfg.rate_bits = rate_bits
             best = None
-            for rep in range(2):   # first pass warms the allocator and twiddle tables
+            try:
+              for rep in range(2 if logn <= 21 else 1):   # first pass warms the allocator and twiddle tables (2^22: one pass, tables come from the previous sizes)
                 ctx.kernel_timing(True)
                 t0 = time.perf_counter()
                 tr = stark.generate_trace(ios)
                 ctx.synchronize()
                 t1 = time.perf_counter()
-                proof = sbn.prove(stark, cfg, tr, np.zeros(0, dtype=np.uint64))
+                try:
+                    proof = sbn.prove(stark, cfg, tr, np.zeros(0, dtype=np.uint64))
+                finally:
+                    tr.free()
                 t2 = time.perf_counter()
-                tr.free()
                 ks = ctx.kernel_stats()
                 ctx.kernel_timing(False)
-                best = (t1 - t0, t2 - t1, proof.timings, ks, len(proof.to_bytes()))
-            tg, tp, ph, ks, plen = best
+                best = (t1 - t0, t2 - t1, proof.timings, ks, len(proof.to_bytes()), hashlib.sha256(proof.to_bytes()).hexdigest()[:16])
+            except sbn.SbnError as e:
+                print(json.dumps({"rows_log2": logn, "rate_bits": rate_bits, "error": str(e)[:200]}), flush=True)
+                continue
+            tg, tp, ph, ks, plen, sha = best
             ntt_ms = sum(ks.get(k, {"ms": 0})["ms"] for k in ("ntt_pass1", "ntt_pass2", "ntt_small"))
             ntt_bytes = 8 * ((C + PAIRS) * (2 * n + 2 * L) + Q * 2 * L)    # iNTT read+write, LDE read (per coset) + write
             leaf_ms = ks.get("merkle_leaf_hash", {"ms": 0})["ms"]
@@ -85,7 +88,8 @@ def run(max_log, min_log):
                                             - ph.get("compute permutation Z polys", 0) - ph["compute quotient polys"], 2),
                    "ntt_kernels_ms": round(ntt_ms, 2), "ntt_hbm_frac": round(ntt_bytes / (ntt_ms / 1e3) / 1e9 / hbm, 4) if ntt_ms else None,
                    "leaf_hash_ms": round(leaf_ms, 2), "poseidon_mperm_s": round(perms / (leaf_ms / 1e3) / 1e6, 1) if leaf_ms else None,
-                   "proof_bytes": plen, "device_gb": round(ctx.device_bytes / 1e9, 2)}
+                   "proof_bytes": plen, "proof_sha256": sha, "device_gb": round(ctx.device_bytes / 1e9, 2),
+                   "streamed": 8.0 * n * ((C + PAIRS) * (1 + (1 << rate_bits)) + PAIRS) * 1.1 > 0.8 * 191.5e9 - 8.0 * n * C}
             print(json.dumps(out), flush=True)
 
 
