@@ -17,7 +17,11 @@ pub const SBN_BATCH_FILL_OUTPUTS: u32 = 2;
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)]
 pub struct sbn_config {
     pub security_bits: u32, pub num_challenges: u32, pub rate_bits: u32, pub cap_height: u32, pub pow_bits: u32,
-    pub fri_arity_bits: u32, pub fri_final_poly_bits: u32, pub num_query_rounds: u32, pub coset_shift: u64,
+    pub fri_arity_bits: u32, pub fri_final_poly_bits: u32, pub num_query_rounds: u32,
+    /// U1: `F::coset_shift()`; the two-adic generator follows as g^((p-1)/2^32).  0 / 7 = (7, 1753635133440165772); 14293326489335486720 = the other candidate pair.
+    pub coset_shift: u64,
+    /// U3: 1 = FRI polynomial multiplied by X (the older "max-degree hack"); 0 = padded batch quotients.
+    pub fri_degree_hack: u32, pub reserved: u32,
 }
 /// AIR identifiers (a generic `Stark` callback cannot cross to CUDA).
 pub const SBN_AIR_MODULAR: i32 = 0;
@@ -57,6 +61,7 @@ extern "C" {
     pub fn sbn_ctx_destroy(ctx: *mut sbn_ctx);
     pub fn sbn_last_error(ctx: *const sbn_ctx) -> *const c_char;
     pub fn sbn_ctx_synchronize(ctx: *mut sbn_ctx) -> i32;
+    pub fn sbn_ctx_select_field(ctx: *mut sbn_ctx, coset_shift: u64) -> i32;
     pub fn sbn_ctx_launch_count(ctx: *const sbn_ctx) -> u64;
     pub fn sbn_ctx_device_bytes(ctx: *const sbn_ctx) -> u64;
     pub fn sbn_ctx_kernel_timing(ctx: *mut sbn_ctx, enable: i32) -> i32;

@@ -28,7 +28,14 @@ typedef struct sbn_proof sbn_proof; /* StarkProofWithPublicInputs in the canonic
 /* mirrors starky::config::StarkConfig (+ FriConfig); see sbn_config_standard_fast */
 typedef struct {
   uint32_t security_bits, num_challenges, rate_bits, cap_height, pow_bits, fri_arity_bits, fri_final_poly_bits, num_query_rounds;
-  uint64_t coset_shift; /* 0 or 7: F::coset_shift() of plonky2_field's Goldilocks */
+  /* U1 -- F::coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR g of plonky2_field's Goldilocks; the two-adic
+   * generator follows as POWER_OF_TWO_GENERATOR = g^((p - 1) / 2^32).  0 or 7: pair (B) = (7, 1753635133440165772), the default;
+   * 14293326489335486720: pair (A) = (.., 7277203076849721926).  Any generator of F* is accepted. */
+  uint64_t coset_shift;
+  /* U3 -- 0: batch quotients padded with `quotient.coeffs.push(0)` (default); 1: the older "max-degree hack", the FRI polynomial
+   * multiplied by X (prover `final_poly.coeffs.insert(0, 0)`, verifier `sum * subgroup_x`). */
+  uint32_t fri_degree_hack;
+  uint32_t reserved; /* must be 0 */
 } sbn_config;
 
 /* AIR identifiers: the `Stark` implementations of the reference */
@@ -79,6 +86,9 @@ int sbn_ctx_create(int device, void* cuda_stream, sbn_ctx** out);
 void sbn_ctx_destroy(sbn_ctx* ctx);
 const char* sbn_last_error(const sbn_ctx* ctx); /* ctx may be NULL: last error of a failed sbn_ctx_create */
 int sbn_ctx_synchronize(sbn_ctx* ctx);
+/* Generator pair (sbn_config.coset_shift semantics) for the stage entry points that take no config (sbn_commit_columns);
+ * sbn_prove / sbn_prove_batch select it from their config. */
+int sbn_ctx_select_field(sbn_ctx* ctx, uint64_t coset_shift);
 uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx);  /* kernels launched so far through this context */
 uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx);  /* bytes held by the context's caching allocator */
 /* Optional CUDA-event timing of the kernel families on the context's stream.  enable != 0 starts (and

@@ -21,11 +21,20 @@ namespace orc { FieldParams g_field; }
 
 enum { AIR_MODULAR = 0, AIR_FQ_EXP = 1, AIR_G1_EXP = 2, AIR_G2_EXP = 3, AIR_FQ12_EXP = 4, AIR_FQ12_EXP_U64 = 5, AIR_G1_MULADD = 6, AIR_FQ12_MUL = 7 };
 
-struct OrcConfig { uint32_t security_bits, num_challenges, rate_bits, cap_height, pow_bits, fri_arity_bits, fri_final_poly_bits, num_query_rounds; uint64_t coset_shift; };
+struct OrcConfig { uint32_t security_bits, num_challenges, rate_bits, cap_height, pow_bits, fri_arity_bits, fri_final_poly_bits, num_query_rounds; uint64_t coset_shift;
+                   uint32_t fri_degree_hack, reserved; };
+// U1: the coset shift is the field's multiplicative generator g and the two-adic generator is
+// g^((p - 1) / 2^32); 0 or 7 selects plonky2_field pair (B) = (7, 1753635133440165772), 14293326489335486720 pair (A).
+static void select_field(const OrcConfig* c) {
+  const u64 g = (c && c->coset_shift) ? c->coset_shift : 7;
+  const GF r = gl_pow(GF(g), 0xFFFFFFFFULL);   // (p - 1) / 2^32 = 2^32 - 1
+  if (gl_exp_pow2(r, 31).v != 0xFFFFFFFF00000000ULL) throw std::runtime_error("coset_shift is not a generator of the multiplicative group (its two-adic part has order < 2^32)");
+  g_field.mult_generator = g; g_field.pow2_generator = r.v;
+}
 static StarkConfig to_cfg(const OrcConfig* c) {
   StarkConfig s;
   if (c) { s.security_bits = c->security_bits; s.num_challenges = c->num_challenges; s.rate_bits = c->rate_bits; s.cap_height = c->cap_height; s.pow_bits = c->pow_bits;
-           s.arity_bits = c->fri_arity_bits; s.final_poly_bits = c->fri_final_poly_bits; s.num_query_rounds = c->num_query_rounds; }
+           s.arity_bits = c->fri_arity_bits; s.final_poly_bits = c->fri_final_poly_bits; s.num_query_rounds = c->num_query_rounds; s.fri_degree_hack = c->fri_degree_hack != 0; }
   return s;
 }
 struct AirHandle { int id; size_t num_io; std::unique_ptr<Air> air; };
@@ -186,7 +195,7 @@ int orc_generate_public_inputs(void* p, const void* ios, size_t num_io, u64* out
 int orc_prove(void* p, const u64* trace, size_t nrows, const u64* pis, size_t npis, const OrcConfig* c, uint8_t** proof_out, size_t* len_out) {
   AirHandle* h = (AirHandle*)p;
   try {
-    if (c && c->coset_shift) g_field.mult_generator = c->coset_shift;
+    select_field(c);
     size_t nc = h->air->num_columns();
     std::vector<std::vector<GF>> cols(nc, std::vector<GF>(nrows));
     for (size_t k = 0; k < nc; k++) for (size_t r = 0; r < nrows; r++) cols[k][r] = GF(trace[k * nrows + r]);
@@ -199,11 +208,15 @@ int orc_prove(void* p, const u64* trace, size_t nrows, const u64* pis, size_t np
   } catch (std::exception& e) { g_err = e.what(); return -2; }
 }
 void orc_free(void* p) { free(p); }
+// selects the generator pair for the stage entry points that take no config (orc_fft, orc_commit_columns, orc_root_of_unity)
+int orc_select_field(u64 coset_shift) {
+  try { OrcConfig c; memset(&c, 0, sizeof c); c.coset_shift = coset_shift; select_field(&c); return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 // verify: 0 = accepted, 1 = rejected (reason in orc_last_error), <0 = malformed input
 int orc_verify(void* p, const uint8_t* proof, size_t len, const OrcConfig* c) {
   AirHandle* h = (AirHandle*)p;
   try {
-    if (c && c->coset_shift) g_field.mult_generator = c->coset_shift;
+    select_field(c);
     Proof pr = deserialize_proof(proof, len);
     std::string r = verify_stark_proof(*h->air, pr, to_cfg(c));
     if (r.empty()) return 0;

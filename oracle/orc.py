@@ -14,11 +14,11 @@ AIR_MODULAR, AIR_FQ_EXP, AIR_G1_EXP, AIR_G2_EXP, AIR_FQ12_EXP, AIR_FQ12_EXP_U64,
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("security_bits", "num_challenges", "rate_bits", "cap_height", "pow_bits",
-                                          "fri_arity_bits", "fri_final_poly_bits", "num_query_rounds")] + [("coset_shift", C.c_uint64)]
+                                          "fri_arity_bits", "fri_final_poly_bits", "num_query_rounds")] + [("coset_shift", C.c_uint64), ("fri_degree_hack", C.c_uint32), ("reserved", C.c_uint32)]
 
     @staticmethod
-    def standard_fast_config(rate_bits=1):
-        return Config(100, 2, rate_bits, 4, 16, 4, 5, 84, 7)
+    def standard_fast_config(rate_bits=1, coset_shift=7, fri_degree_hack=0):
+        return Config(100, 2, rate_bits, 4, 16, 4, 5, 84, coset_shift, fri_degree_hack, 0)
 
 
 def build(force=False):
@@ -63,6 +63,12 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def select_field(coset_shift=7):
+    """U1: generator pair used by the stage entry points without a config (fft, commit_columns, root of unity); 7 = default."""
+    if lib().orc_select_field(C.c_uint64(coset_shift)) != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
 
 
 def set_threads(n):

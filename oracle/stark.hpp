@@ -20,6 +20,9 @@ namespace orc {
 struct StarkConfig {  // StarkConfig::standard_fast_config
   int security_bits = 100, num_challenges = 2;
   int rate_bits = 1, cap_height = 4, pow_bits = 16, arity_bits = 4, final_poly_bits = 5, num_query_rounds = 84;
+  // U3: false = `quotient.coeffs.push(0)` padding (B.8); true = the older "max-degree hack" -- the batch quotients
+  // are not padded and the FRI polynomial is multiplied by X (prover `final_poly.coeffs.insert(0, 0)`, verifier `sum * subgroup_x`).
+  bool fri_degree_hack = false;
   std::vector<int> reduction_arity_bits(int degree_bits) const {  // FriReductionStrategy::ConstantArityBits
     std::vector<int> r;
     while (degree_bits > final_poly_bits && degree_bits + rate_bits - arity_bits >= cap_height) { r.push_back(arity_bits); degree_bits -= arity_bits; }
@@ -376,6 +379,9 @@ static inline Proof prove(const Air& air, const StarkConfig& cfg, const std::vec
     if (final_poly.empty()) final_poly.assign(degree, GF2());
     for (size_t i = 0; i < degree; i++) final_poly[i] = final_poly[i] * shift + quot[i];
   }
+  if (cfg.fri_degree_hack) {   // coefficient degree-1 of every padded quotient is zero, so the product with X still has `degree` coefficients
+    final_poly.insert(final_poly.begin(), GF2()); final_poly.pop_back();
+  }
   std::vector<GF2> lde_coeffs = final_poly; lde_coeffs.resize(degree << rate_bits);
   std::vector<GF2> lde_values = coset_fft_ext(lde_coeffs, coset_shift());
   tms["fri_reduce"] = tm.lap();
@@ -538,6 +544,7 @@ static inline std::string verify_stark_proof(const Air& air, const Proof& proof,
       sum = sum * gf2_pow(fri_alpha, ev.size());
       sum = sum + numerator * gf2_inv(denominator);
     }
+    if (cfg.fri_degree_hack) sum = sum * subgroup_x;
     GF2 old_eval = sum;
     for (size_t i = 0; i < arities.size(); i++) {
       int ab = arities[i]; size_t arity = size_t(1) << ab;

@@ -31,7 +31,7 @@ class StarkConfig(C.Structure):
     """starky::config::StarkConfig (+ FriConfig).  `standard_fast_config` is what every reference call
     site uses (reference src/curves/g1/exp.rs:250-253)."""
     _fields_ = [(n, C.c_uint32) for n in ("security_bits", "num_challenges", "rate_bits", "cap_height", "pow_bits",
-                                          "fri_arity_bits", "fri_final_poly_bits", "num_query_rounds")] + [("coset_shift", C.c_uint64)]
+                                          "fri_arity_bits", "fri_final_poly_bits", "num_query_rounds")] + [("coset_shift", C.c_uint64), ("fri_degree_hack", C.c_uint32), ("reserved", C.c_uint32)]
 
     @staticmethod
     def standard_fast_config(num_columns=None, num_public_inputs=None):
@@ -67,6 +67,7 @@ def lib():
         L.sbn_last_error.restype = C.c_char_p
         L.sbn_last_error.argtypes = [vp]
         L.sbn_ctx_synchronize.argtypes = [vp]
+        L.sbn_ctx_select_field.argtypes = [vp, C.c_uint64]
         L.sbn_ctx_launch_count.restype = C.c_uint64
         L.sbn_ctx_launch_count.argtypes = [vp]
         L.sbn_ctx_device_bytes.restype = C.c_uint64
@@ -123,6 +124,10 @@ class Context:
 
     def synchronize(self):
         self.check(lib().sbn_ctx_synchronize(self.h))
+
+    def select_field(self, coset_shift=7):
+        """U1: generator pair for the stage entry points without a config (commit_columns); prove() takes it from the config."""
+        self.check(lib().sbn_ctx_select_field(self.h, coset_shift))
 
     @property
     def launch_count(self):

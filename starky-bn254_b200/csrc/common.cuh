@@ -37,6 +37,21 @@ struct NttTables {  // for domain size N = 2^logn: powers of w_N and w_N^-1 (N e
 // stream is synchronised, and only then is the pointer published under the mutex, so any other stream may read it.
 struct SharedTables {
   std::mutex mu;
+  // U1: multiplicative generator = coset shift, and the generator of the 2^32 roots of unity derived
+  // from it as g^((p - 1) / 2^32).  Default: plonky2_field pair (B) = (7, 1753635133440165772).  Tables depend on the pair.
+  u64 mult_gen = GL_MULT_GENERATOR, pow2_gen = GL_POW2_GENERATOR;
+  void select_generator(u64 g) {   // callers hold no table pointers across this (start of a prove / batch call)
+    if (g == 0) g = GL_MULT_GENERATOR;
+    std::lock_guard<std::mutex> lk(mu);
+    if (g == mult_gen) return;
+    const u64 r = gl_pow(g, 0xFFFFFFFFULL);   // (p - 1) / 2^32 = 2^32 - 1
+    if (g >= GL_P || gl_exp_pow2(r, 31) != GL_P - 1) throw SbnError(SBN_ERR_INVALID, "coset_shift is not a generator of the multiplicative group (two-adic part of order < 2^32)");
+    cudaDeviceSynchronize();
+    for (auto& kv : pow_tables) cudaFree(kv.second);
+    for (auto& kv : fourstep_tables) cudaFree(kv.second);
+    pow_tables.clear(); fourstep_tables.clear(); ntt_tables.clear();
+    mult_gen = g; pow2_gen = r;
+  }
   std::map<int, NttTables> ntt_tables;
   std::map<std::tuple<int, bool, u64>, u64*> fourstep_tables;   // (logn, inverse, coset base) -> ntt.cu F table
   std::map<std::pair<u64, int>, u64*> pow_tables;               // (base, logn) -> base^i, i < 2^logn
@@ -87,6 +102,8 @@ struct sbn_ctx {
     pinned_used += need;
   }
   void begin_call() { pinned_used = 0; }
+  u64 coset_shift() const { return tables->mult_gen; }
+  u64 root_of_unity(int logn) const { return gl_exp_pow2(tables->pow2_gen, 32 - logn); }
   // caching allocator
   struct Block { void* p; size_t bytes; bool used; };
   std::vector<Block> blocks;

@@ -42,7 +42,7 @@ NttTables get_ntt_tables(sbn_ctx* ctx, int logn) {
   auto it = T.ntt_tables.find(logn);
   if (it != T.ntt_tables.end()) return it->second;
   NttTables t; t.logn = logn;
-  u64 w = gl_root_of_unity(logn);
+  u64 w = ctx->root_of_unity(logn);
   t.w_fwd = (u64*)pow_table_locked(ctx, w, logn);
   t.w_inv = (u64*)pow_table_locked(ctx, gl_inv(w), logn);
   T.ntt_tables[logn] = t;
@@ -240,7 +240,7 @@ static const u64* get_fourstep_table(sbn_ctx* ctx, int logn, bool inverse, u64 c
   if (it != T.fourstep_tables.end()) return it->second;
   const size_t n = size_t(1) << logn;
   const int l1 = logn / 2, l2 = logn - l1;
-  u64 w = gl_root_of_unity(logn);
+  u64 w = ctx->root_of_unity(logn);
   if (inverse) w = gl_inv(w);
   u64* p; CUDA_CHECK(cudaMalloc(&p, n * 8));
   k_fourstep_table<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, w, c ? c : 1, inverse ? gl_inv((u64)n) : 1, l2, n);
@@ -365,9 +365,9 @@ void intt_columns(sbn_ctx* ctx, const u64* values, u64* coeffs, int ncols, int l
 void lde_columns(sbn_ctx* ctx, const u64* coeffs, u64* lde, int ncols, int logn, int rate_bits) {
   size_t N = size_t(1) << logn;
   int R = 1 << rate_bits;
-  u64 wL = gl_root_of_unity(logn + rate_bits);
+  u64 wL = ctx->root_of_unity(logn + rate_bits);
   for (int b = 0; b < R; b++) {
-    u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, b));
+    u64 sb = gl_mul(ctx->coset_shift(), gl_pow(wL, b));
     ntt_batch(ctx, coeffs, N, lde + (size_t)b * N, N * R, ncols, logn, false, sb, nullptr);
   }
 }
@@ -375,7 +375,7 @@ void lde_columns(sbn_ctx* ctx, const u64* coeffs, u64* lde, int ncols, int logn,
 // One sub-coset b of the LDE: out[col][k] = value at natural LDE index k 2^r + b (column stride N).
 void lde_sub_coset(sbn_ctx* ctx, const u64* coeffs, u64* out, int ncols, int logn, int rate_bits, int b) {
   size_t N = size_t(1) << logn;
-  const u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(gl_root_of_unity(logn + rate_bits), (u64)b));
+  const u64 sb = gl_mul(ctx->coset_shift(), gl_pow(ctx->root_of_unity(logn + rate_bits), (u64)b));
   ntt_batch(ctx, coeffs, N, out, N, ncols, logn, false, sb, nullptr);
 }
 
@@ -397,18 +397,18 @@ __global__ void k_fold_mod_binomial(const u64* __restrict__ coeffs, size_t N, u6
 void lde_class(sbn_ctx* ctx, const u64* coeffs, u64* out, int ncols, int logn, int rate_bits, int m, u32 rho) {
   const size_t N = size_t(1) << logn;
   const int R = 1 << rate_bits, G = 1 << m;
-  const u64 wL = gl_root_of_unity(logn + rate_bits);
+  const u64 wL = ctx->root_of_unity(logn + rate_bits);
   if (G <= R) {
     const int Bp = R / G;
     for (int bp = 0; bp < Bp; bp++) {
-      const u64 sb = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, rho + (u64)G * bp));
+      const u64 sb = gl_mul(ctx->coset_shift(), gl_pow(wL, rho + (u64)G * bp));
       ntt_batch(ctx, coeffs, N, out + (size_t)bp * N, N * Bp, ncols, logn, false, sb, nullptr);
     }
     return;
   }
   const int logLp = logn + rate_bits - m, f = G / R;
   const size_t Lp = size_t(1) << logLp;
-  const u64 c = gl_mul(GL_MULT_GENERATOR, gl_pow(wL, rho));
+  const u64 c = gl_mul(ctx->coset_shift(), gl_pow(wL, rho));
   DevBuf<u64> folded(ctx, (size_t)ncols * Lp);
   { KScope ks(ctx, "lde_fold");
     k_fold_mod_binomial<<<dim3((unsigned)((Lp + 255) / 256), (unsigned)ncols), 256, 0, ctx->stream>>>(coeffs, N, folded, Lp, f, gl_exp_pow2(c, logLp));

@@ -179,8 +179,9 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   const int logn = tr->logn, rate_bits = cfg.rate_bits, cap_height = cfg.cap_height, nch = cfg.num_challenges;
   const size_t N = size_t(1) << logn, L = N << rate_bits;
   SBN_REQUIRE(npis == air.num_public_inputs, "public input count mismatch");
-  SBN_REQUIRE(cfg.coset_shift == 0 || cfg.coset_shift == GL_MULT_GENERATOR, "unsupported coset shift");
+  SBN_REQUIRE(cfg.coset_shift == 0 ? ctx->coset_shift() == GL_MULT_GENERATOR : cfg.coset_shift == ctx->coset_shift(), "internal: generator pair not selected");
   SBN_REQUIRE(nch >= 1 && nch <= SBN_MAX_CHALLENGES, "unsupported num_challenges");
+  SBN_REQUIRE(cfg.fri_degree_hack <= 1 && cfg.reserved == 0, "bad config flags");
   SBN_REQUIRE(logn + rate_bits <= 30 && rate_bits >= 1 && rate_bits <= 4, "unsupported trace size / rate");
   SBN_REQUIRE(cap_height <= logn + rate_bits && cfg.pow_bits >= 1, "bad FRI configuration");
   std::vector<int> arities = reduction_arity_bits(cfg, logn);
@@ -343,7 +344,7 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
 
   // ---- openings ----
   gl2 zeta = ch.get_ext();
-  u64 g = gl_root_of_unity(logn);
+  u64 g = ctx->root_of_unity(logn);
   if (gl2_eq(gl2_pow(zeta, (u64)N), gl2_make(1, 0))) throw SbnError(SBN_ERR_INTERNAL, "Opening point is in the subgroup.");
   gl2 zeta_next = gl2_mul_base(zeta, g);
   const int C = (int)air.num_columns, Z = uses_perm ? z_c.ncols : 0;
@@ -395,8 +396,15 @@ static void prove_impl(sbn_ctx* ctx, const sbn_config& cfg, const sbn_trace* tr,
   DevBuf<u64> fcoeffs(ctx, 2 * L), fvalues(ctx, 2 * L);
   ColumnSplit split{sh.rank, sh.world, [&](const void* a, size_t n, void* b) { sh.gather_device(ctx, a, n, b); }};
   fri_final_poly(ctx, views, logn, rate_bits, fri_alpha, zeta, zeta_next, fcoeffs, sh.on() && sh.allgather_device ? &split : nullptr, zpw);
+  if (cfg.fri_degree_hack) {   // U3: multiply the FRI polynomial by X (its top coefficient is zero: the batch quotients were padded)
+    DevBuf<u64> shifted(ctx, 2 * L);
+    CUDA_CHECK(cudaMemsetAsync(shifted, 0, 2 * L * 8, ctx->stream));
+    for (int comp = 0; comp < 2; comp++)
+      CUDA_CHECK(cudaMemcpyAsync(shifted + (size_t)comp * L + 1, fcoeffs + (size_t)comp * L, (N - 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    fcoeffs = std::move(shifted);
+  }
   tm.mark("reduce batch of polynomials");
-  u64 shift = GL_MULT_GENERATOR;
+  u64 shift = ctx->coset_shift();
   ntt_batch(ctx, fcoeffs, L, fvalues, L, 2, logL, false, shift, nullptr);
   tm.mark("perform final FFT");
   std::vector<FriLayer> layers(arities.size());
@@ -555,6 +563,7 @@ void sbn_ctx_destroy(sbn_ctx* ctx) {
   ctx_delete(ctx);
 }
 const char* sbn_last_error(const sbn_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+int sbn_ctx_select_field(sbn_ctx* ctx, uint64_t coset_shift) { API_BEGIN SBN_REQUIRE(ctx, "null context"); CUDA_CHECK(cudaSetDevice(ctx->device)); ctx->tables->select_generator(coset_shift); API_END(ctx) }
 int sbn_ctx_synchronize(sbn_ctx* ctx) { API_BEGIN SBN_REQUIRE(ctx, "null context"); CUDA_CHECK(cudaSetDevice(ctx->device)); ctx->sync(); API_END(ctx) }
 uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx) { return ctx->launches; }
 uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx) { return ctx->bytes_allocated; }
@@ -580,7 +589,7 @@ int sbn_ctx_kernel_stats(sbn_ctx* ctx, char* buf, size_t cap) {
 }
 int sbn_config_standard_fast(sbn_config* out) {
   if (!out) return -1;
-  *out = sbn_config{100, 2, 1, 4, 16, 4, 5, 84, GL_MULT_GENERATOR};
+  *out = sbn_config{100, 2, 1, 4, 16, 4, 5, 84, GL_MULT_GENERATOR, 0, 0};
   return 0;
 }
 int sbn_air_info(int air, size_t num_io, size_t* num_columns, size_t* num_public_inputs, size_t* num_rows, size_t* io_size, size_t* result_words,
@@ -665,6 +674,7 @@ int sbn_prove(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* trace, co
   SBN_REQUIRE(trace->ctx == ctx, "trace belongs to another context");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   ctx->begin_call();
+  ctx->tables->select_generator(config->coset_shift);
   std::unique_ptr<sbn_proof> p(new sbn_proof());
   prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, Shard(), p.get());
   *out = p.release();
@@ -680,6 +690,7 @@ int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* t
   Shard sh; sh.rank = (int)shard->rank; sh.world = (int)shard->world; sh.allgather = shard->allgather; sh.user = shard->user; sh.allgather_device = shard->allgather_device;
   while ((1 << sh.m) < sh.world) sh.m++;
   ctx->begin_call();
+  ctx->tables->select_generator(config->coset_shift);
   std::unique_ptr<sbn_proof> p(new sbn_proof());
   prove_impl(ctx, *config, trace, (const u64*)public_inputs, num_public_inputs, sh, p.get());
   *out = p.release();
@@ -748,6 +759,8 @@ int sbn_prove_batch(sbn_batch* b, int air_id, size_t num_io, const sbn_config* c
     SBN_REQUIRE(config && ios && proofs_out, "null argument");
     const AirDesc air = make_air(air_id, num_io);
     for (size_t j = 0; j < count; j++) { SBN_REQUIRE(ios[j], "null input batch"); proofs_out[j] = nullptr; }
+    CUDA_CHECK(cudaSetDevice(b->device));
+    b->lanes[0]->tables->select_generator(config->coset_shift);   // one table set for all lanes; no lane is running yet
     std::vector<std::unique_ptr<sbn_proof>> proofs(count);
     std::atomic<size_t> next(0);
     std::atomic<bool> failed(false);

@@ -326,22 +326,22 @@ void quotient_eval(sbn_ctx* ctx, const AirDesc& air, const QDomain& dom, const u
   SBN_REQUIRE(dom.m <= logn, "too many quotient classes");
   const size_t N = size_t(1) << logn, R = size_t(1) << rate_bits, L = N * R;
   const size_t step = size_t(1) << (rate_bits - 1);
-  const u64 w2n = gl_root_of_unity(logn + 1);
+  const u64 w2n = ctx->root_of_unity(logn + 1);
   QArgs a; memset(&a, 0, sizeof a);
   a.logn = logn;
   if (dom.m == 0) {   // two half-cosets inside the LDE batches
     a.logm = logn; a.nseg = 2; a.npoints = 2 * N; a.next_shift = 1;
     a.trace = a.trace_next = trace_lde; a.trace_stride = L; a.zs = a.zs_next = zs_lde; a.zs_stride = L;
-    for (int bq = 0; bq < 2; bq++) { a.seg_off[bq] = (size_t)bq * step * N; a.seg_shift[bq] = gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, bq)); }
+    for (int bq = 0; bq < 2; bq++) { a.seg_off[bq] = (size_t)bq * step * N; a.seg_shift[bq] = gl_mul(ctx->coset_shift(), gl_pow(w2n, bq)); }
   } else {            // one class of 2^m: its own batch, "next" in the same batch (G = 2) or in the class + 2 batch
     const u32 G = 1u << dom.m;
     a.logm = logn + 1 - dom.m; a.nseg = 1; a.npoints = size_t(1) << a.logm;
     a.trace = dom.trace; a.trace_next = dom.trace_next; a.trace_stride = a.npoints;
     a.zs = dom.zs; a.zs_next = dom.zs_next; a.zs_stride = a.npoints;
     a.next_shift = G == 2 ? 1 : (dom.sigma + 2 >= G ? 1 : 0);
-    a.seg_off[0] = 0; a.seg_shift[0] = gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, dom.sigma));
+    a.seg_off[0] = 0; a.seg_shift[0] = gl_mul(ctx->coset_shift(), gl_pow(w2n, dom.sigma));
   }
-  a.wpow = get_ntt_tables(ctx, a.logm).w_fwd; a.w_inv = gl_inv(gl_root_of_unity(logn));
+  a.wpow = get_ntt_tables(ctx, a.logm).w_fwd; a.w_inv = gl_inv(ctx->root_of_unity(logn));
   // Lagrange selectors on the evaluation points
   const NttTables& tb = get_ntt_tables(ctx, logn);
   DevBuf<u64> lag_coeffs(ctx, 2 * N), lag_lde(ctx, dom.m == 0 ? 2 * L : 2 * a.npoints);
@@ -387,12 +387,12 @@ void quotient_eval(sbn_ctx* ctx, const AirDesc& air, const QDomain& dom, const u
 // per-coset interpolation (coset_ifft restricted to each half), then split into the two chunks
 void quotient_finish(sbn_ctx* ctx, const u64* d_acc, int num_challenges, int logn, u64* out_chunks) {
   const size_t N = size_t(1) << logn;
-  const u64 w2n = gl_root_of_unity(logn + 1), gn = gl_exp_pow2(GL_MULT_GENERATOR, logn);
+  const u64 w2n = ctx->root_of_unity(logn + 1), gn = gl_exp_pow2(ctx->coset_shift(), logn);
   DevBuf<u64> u(ctx, 2 * N);
   u64 inv2 = gl_inv(2), inv2gn = gl_inv(gl_mul(2, gn));
   for (int c = 0; c < num_challenges; c++) {
     for (int bq = 0; bq < 2; bq++) {
-      const u64* post = get_pow_table(ctx, gl_inv(gl_mul(GL_MULT_GENERATOR, gl_pow(w2n, bq))), logn);
+      const u64* post = get_pow_table(ctx, gl_inv(gl_mul(ctx->coset_shift(), gl_pow(w2n, bq))), logn);
       ntt_batch(ctx, d_acc + ((size_t)c * 2 + bq) * N, N, u + (size_t)bq * N, N, 1, logn, true, 0, post);
     }
     k_quotient_split<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(u, u + N, out_chunks + (size_t)(2 * c) * N, out_chunks + (size_t)(2 * c + 1) * N, inv2, inv2gn, N);

@@ -489,3 +489,45 @@ def test_ntt_size_2_25(ctx):
     cfl, ldel, _ = ctx.commit_columns(lin, 1, 4)
     assert int(cfl[0][0]) == c0 and not cfl[0][1:].any() and (ldel == c0).all()
     assert w_n and c1
+
+
+@pytest.mark.parametrize("coset_shift,hack", [(14293326489335486720, 0), (7, 1), (14293326489335486720, 1)])
+def test_uncertainty_switches_match_oracle(ctx, sbn, orc, coset_shift, hack):
+    """U1 / U3 (SURVEY.md B.13): the generator pair and the FRI degree hack are switches shared by the GPU prover and the oracle;
+    for every setting the GPU proof equals the oracle's bytes and the oracle's verifier accepts it under the same setting only."""
+    n = 512
+    ios = sbn.synthetic.modular_ios(n)
+    stark = sbn.ModularStark(n, ctx)
+    cfg = stark.config()
+    cfg.coset_shift, cfg.fri_degree_hack = coset_shift, hack
+    tr = stark.generate_trace(ios)
+    pi = np.zeros(0, dtype=np.uint64)
+    got = sbn.prove(stark, cfg, tr, pi).to_bytes()
+    air = orc.Air(orc.AIR_MODULAR, n)
+    ocfg = orc.Config.standard_fast_config(coset_shift=coset_shift, fri_degree_hack=hack)
+    otrace, _ = air.generate_trace(ios)
+    assert got == air.prove(otrace, pi, ocfg)
+    assert air.verify(got, ocfg) == (True, "")
+    assert not air.verify(got)[0]
+    # back to the default pair on the same context: tables are rebuilt and the golden proof comes out again
+    back = sbn.prove(stark, stark.config(), tr, pi).to_bytes()
+    tr.free()
+    assert back == air.prove(otrace, pi)
+    # stage entry point under pair (A)
+    if coset_shift != 7 and not hack:
+        rng = np.random.default_rng(3)
+        vals = rng.integers(0, P, size=(5, 1 << 12), dtype=np.uint64)
+        ctx.select_field(coset_shift); orc.select_field(coset_shift)
+        try:
+            coeffs, lde, cap = ctx.commit_columns(vals, 1, 4)
+            oc, ol, ocap = orc.commit_columns(vals, 1, 4)
+        finally:
+            ctx.select_field(7); orc.select_field(7)
+        assert (coeffs == oc).all() and (lde == ol).all() and (cap == ocap).all()
+    with pytest.raises(sbn.SbnError):
+        bad = stark.config(); bad.coset_shift = 49
+        t2 = stark.generate_trace(ios)
+        try:
+            sbn.prove(stark, bad, t2, pi)
+        finally:
+            t2.free()

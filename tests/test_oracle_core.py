@@ -235,3 +235,36 @@ def test_gadget_airs_prove_verify_tamper_and_golden(orc, sbn, golden, name, air_
         assert not air.verify(bytes(b))[0], "tampered proof accepted at byte %d" % pos
     t2 = trace.copy(); t2[70][9] ^= 1
     assert orc.check_trace(air, t2, np.zeros(0, dtype=np.uint64))[0] > 0
+
+
+GEN_A = 14293326489335486720   # SURVEY.md App. C candidate pair (A): (14293326489335486720, 7277203076849721926)
+
+
+def test_uncertainty_switches_u1_u3_round_trip_and_cross_reject(orc, sbn):
+    """U1 (generator pair) and U3 (FRI degree hack) are real switches of oracle prover + verifier: each setting verifies under
+    itself and is rejected under any other, and every setting changes the proof bytes (so a differential test against the real
+    crates can tell them apart).  The pair is derived from the coset shift: two-adic generator = g^((p - 1) / 2^32)."""
+    assert pow(GEN_A, (P - 1) >> 32, P) == 7277203076849721926
+    assert pow(7277203076849721926, 1 << 31, P) == P - 1
+    n = 512
+    ios = sbn.synthetic.modular_ios(n)
+    air = orc.Air(orc.AIR_MODULAR, n)
+    trace, _ = air.generate_trace(ios)
+    pi = np.zeros(0, dtype=np.uint64)
+    settings = [(7, 0), (GEN_A, 0), (7, 1), (GEN_A, 1)]
+    proofs = {s: air.prove(trace, pi, orc.Config.standard_fast_config(coset_shift=s[0], fri_degree_hack=s[1])) for s in settings}
+    assert len({hashlib.sha256(p).hexdigest() for p in proofs.values()}) == 4
+    for i, s in enumerate(settings):
+        for v in (s, settings[(i + 1) % 4], settings[(i + 2) % 4]):   # itself, and the settings differing in one / both switches
+            ok, _ = air.verify(proofs[s], orc.Config.standard_fast_config(coset_shift=v[0], fri_degree_hack=v[1]))
+            assert ok == (s == v), (s, v)
+    # small roots of unity under (A) are the powers of two SURVEY App. C lists: w_64 = 2^3
+    orc.select_field(GEN_A)
+    try:
+        assert orc.lib().orc_root_of_unity(6) == 8 and orc.lib().orc_root_of_unity(4) == 1 << 12
+    finally:
+        orc.select_field(7)
+    with pytest.raises(RuntimeError):
+        orc.select_field(49)   # a square: not a generator
+    # leave the default pair selected for the rest of the session
+    assert air.verify(proofs[(7, 0)]) == (True, "")
