@@ -58,46 +58,6 @@ HD Fq fq_mul(const Fq& a, const Fq& b) {
   for (int i = 0; i < 8; i++) r.l[i] = t[i];
   return r;
 }
-// Montgomery product with a SHORT dependency chain, for the exponentiation-chain kernels (one warp per scheduler, nothing to
-// hide latency behind: the word-serial CIOS loop of fq_mul above is one ~1300-cycle carry chain).  b is cut into sixteen 16-bit
-// digits, so every partial product a_j * d_i < 2^48 and up to 2^16 of them can be summed in a plain 64-bit column accumulator with
-// IMAD.WIDE's own addend -- no carry handling inside the 128 multiply-adds, which are independent across columns.  acc[p] collects
-// the terms of weight 2^(16 p).  The reduction is Montgomery on 16-bit digits (R = 2^256 as in fq_mul, so both functions return
-// the same canonical element): sixteen steps m = acc[p] * (-p^-1) mod 2^16, acc[p + 2 j] += m * P_j, carry acc[p] >> 16 into
-// acc[p + 1]; only that carry links consecutive steps (~20 cycles each).  Every accumulator stays below 2^53.
-HD Fq fq_mul_lat(const Fq& a, const Fq& b) {
-  const u32 P[8] = FQ_P_LIST;
-  u64 acc[33];
-#pragma unroll
-  for (int p = 0; p < 33; p++) acc[p] = 0;
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const u32 d = (b.l[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[2 * j + i] += (u64)a.l[j] * d;
-  }
-#pragma unroll
-  for (int p = 0; p < 16; p++) {
-    const u32 m = ((u32)acc[p] * (FQ_N0 & 0xFFFFu)) & 0xFFFFu;
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[p + 2 * j] += (u64)m * P[j];
-    acc[p + 1] += acc[p] >> 16;   // the low 16 bits of acc[p] are zero now
-  }
-  // digits 16 .. 31 (+ overflow in acc[32]) -> eight words
-  u32 t[8]; u64 c = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    c += acc[16 + 2 * k]; const u32 lo = (u32)c & 0xFFFFu; c >>= 16;
-    c += acc[17 + 2 * k]; const u32 hi = (u32)c & 0xFFFFu; c >>= 16;
-    t[k] = lo | (hi << 16);
-  }
-  c += acc[32];
-  if (c || fq_geq_p(t)) fq_sub_p(t);   // the result is < 2 p
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.l[i] = t[i];
-  return r;
-}
 HD Fq fq_add(const Fq& a, const Fq& b) {
   u32 t[8]; u64 c = 0;
 #pragma unroll

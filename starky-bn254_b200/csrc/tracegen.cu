@@ -422,8 +422,8 @@ __global__ void __launch_bounds__(32) k_fq_chain(const sbn_fq_exp_io* __restrict
   for (int k = 0; k <= 256; k++) {
     fq_to_words(A, ca + k * 8); fq_to_words(B, cb + k * 8);
     if (k == 256) break;
-    if ((io.exp_val[k >> 5] >> (k & 31)) & 1) B = fq_mul_lat(B, A);
-    A = fq_mul_lat(A, A);
+    if ((io.exp_val[k >> 5] >> (k & 31)) & 1) B = fq_mul(B, A);
+    A = fq_sqr(A);
   }
 }
 // main columns: a16 b16 FqOutput(112) flags14   (reference src/fields/fq/exp.rs:128-178)
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(288) k_fq12_chain(const void* __restrict__ ios
   u32* ca = chain + inst * 2 * (size_t)(nbits + 1) * 96; u32* cb = ca + (size_t)(nbits + 1) * 96;
   for (int k = 0; k <= nbits; k++) {
     const bool bit = k < nbits && fq12_exp_bit(ios, io_size, inst, k, u64_variant);
-    if (k < nbits && (which == 0 || bit)) pr[which][ij] = fq_mul_lat((which ? sb : sa)[pi], sa[pj]);
+    if (k < nbits && (which == 0 || bit)) pr[which][ij] = fq_mul((which ? sb : sa)[pi], sa[pj]);
     if (t >= 32 && t < 56) {   // canonical words of the current values (a separate warp from the summing threads)
       const int c = t - 32;
       fq_to_words((c < 12 ? sa : sb)[c % 12], (c < 12 ? ca : cb) + ((size_t)k * 12 + c % 12) * 8);

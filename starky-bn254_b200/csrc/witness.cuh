@@ -154,7 +154,7 @@ template <class W> HD bool g1_row(const u32* ax, const u32* ay, const u32* bx, c
 // The chain kernels run one warp per scheduler, so nothing hides instruction fetch: with every multiplication inlined
 // one add + double is ~150 KB of code, far beyond the instruction cache.  The formulas therefore call ONE out-of-line
 // copy of the Montgomery product.
-__host__ __device__ __noinline__ Fq fq_mul_call(const Fq& a, const Fq& b) { return fq_mul_lat(a, b); }   // bn254.cuh: short dependency chain
+__host__ __device__ __noinline__ Fq fq_mul_call(const Fq& a, const Fq& b) { return fq_mul(a, b); }
 struct G1Jac { Fq x, y, z; };
 HD Fq fq_sqr_call(const Fq& a) { return fq_mul_call(a, a); }
 HD G1Jac g1_jac_dbl(const G1Jac& p) {

@@ -154,11 +154,4 @@ void emu_fq12_row(const u32* a, const u32* b, const u32* out_words, int op, u64*
   }
 }
 void emu_flags_u64_row(u64 e, int r, u64* out) { flags_u64_row(e, r, out); }
-// both Montgomery products of bn254.cuh on the same operands (Montgomery-form words in, words out)
-void emu_fq_mul_both(const u32* a, const u32* b, u32* out_cios, u32* out_lat) {
-  Fq x, y;
-  for (int i = 0; i < 8; i++) { x.l[i] = a[i]; y.l[i] = b[i]; }
-  Fq r0 = fq_mul(x, y), r1 = fq_mul_lat(x, y);
-  for (int i = 0; i < 8; i++) { out_cios[i] = r0.l[i]; out_lat[i] = r1.l[i]; }
-}
 }

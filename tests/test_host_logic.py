@@ -223,23 +223,6 @@ def test_device_poseidon_mds_digit_model_matches_plain_layer():
             assert [g % P for g in got] == want and all(g < 2**64 for g in got)
 
 
-def test_low_latency_montgomery_product_equals_cios(emu, sbn):
-    """fq_mul_lat (16-bit digits, 64-bit column accumulators, digit-wise Montgomery reduction: the product the exponentiation-chain
-    kernels use) returns the same canonical element as the word-serial CIOS fq_mul, and both equal a b R^-1 mod p."""
-    q = sbn.synthetic.BN254_P
-    rinv = pow(1 << 256, -1, q)
-    rng = random.Random(21)
-    vals = [0, 1, q - 1, q - 2, (1 << 256) % q, 0xFFFFFFFF, (q - 1) // 2] + [rng.randrange(q) for _ in range(300)]
-    o0, o1 = np.zeros(8, dtype=np.uint32), np.zeros(8, dtype=np.uint32)
-    for k in range(len(vals) * 2):
-        a, b = rng.choice(vals), rng.choice(vals)
-        emu.emu_fq_mul_both(vp(_w8(a)), vp(_w8(b)), vp(o0), vp(o1))
-        want = a * b * rinv % q
-        got0 = sum(int(o0[i]) << (32 * i) for i in range(8))
-        got1 = sum(int(o1[i]) << (32 * i) for i in range(8))
-        assert got0 == want and got1 == want, (hex(a), hex(b))
-
-
 def _w8(v):
     return np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
 
