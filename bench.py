@@ -263,6 +263,7 @@ def main():
         osteps = max(4, args.steps // 2)
         for name in ("g2", "fq12", "fq"):
             try:
+                batch.trim()   # the lanes' allocators cache the previous AIR's block sizes
                 ab = AirBench(sbn, torch, batch, local, rank, name, 0)
                 ab.resident(0, lanes)
                 oms, _, _ = timed(ab.resident, 0, osteps)
@@ -358,6 +359,7 @@ def main():
     # ---- latency mode: ONE proof computed by all ranks together (sbn_prove_sharded).  Reported beside the throughput
     # number.  A rank that fails between collectives would leave its peers blocked in NCCL: a watchdog prints the headline line
     # (already complete above) and ends the process if this section does not finish in time. ----
+    batch.trim()
     if world > 1 and world in (2, 4, 8, 16) and not args.no_intra_proof:
         def watchdog():
             if rank == 0 and line is not None:
@@ -398,10 +400,11 @@ def main():
             sh_ms = sharding.max_over_ranks([s0.elapsed_time(s1) / nsh], device="cuda")[0]
             same = sharding.gather_digests({rank: sharded_bytes}, world, device="cuda")
             ok = len({d[0] for d in same}) == 1
+            phases_sh = {k: round(v, 3) for k, v in sharded_phases.items()}   # before the unsharded comparison proof overwrites them
             if rank == 0:
                 ok = ok and hashlib.sha256(step_sharded(single=True)).hexdigest() == same[0][0]
             intra = {"world": world, "ms_per_proof": sh_ms, "proof_identical_on_all_ranks_and_to_unsharded": ok,
-                     "phase_ms_rank0": {k: round(v, 3) for k, v in sharded_phases.items()},
+                     "phase_ms_rank0": phases_sh,
                      "collectives": "NCCL all_gather: 3 x cap digests, opening values (host-staged blocks); quotient values, FRI partial sums, opened rows (device to device)"}
         except Exception as e:   # noqa: BLE001
             intra = {"world": world, "error": "%s: %s" % (type(e).__name__, e)}

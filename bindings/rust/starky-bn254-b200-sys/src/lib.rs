@@ -64,6 +64,7 @@ extern "C" {
     pub fn sbn_ctx_select_field(ctx: *mut sbn_ctx, coset_shift: u64) -> i32;
     pub fn sbn_ctx_launch_count(ctx: *const sbn_ctx) -> u64;
     pub fn sbn_ctx_device_bytes(ctx: *const sbn_ctx) -> u64;
+    pub fn sbn_ctx_trim(ctx: *mut sbn_ctx) -> i32;
     pub fn sbn_ctx_kernel_timing(ctx: *mut sbn_ctx, enable: i32) -> i32;
     pub fn sbn_ctx_kernel_stats(ctx: *mut sbn_ctx, buf: *mut c_char, cap: usize) -> i32;
     pub fn sbn_config_standard_fast(out: *mut sbn_config) -> i32;
@@ -87,6 +88,7 @@ extern "C" {
                            proofs_out: *mut *mut sbn_proof) -> i32;
     pub fn sbn_batch_launch_count(batch: *const sbn_batch) -> u64;
     pub fn sbn_batch_device_bytes(batch: *const sbn_batch) -> u64;
+    pub fn sbn_batch_trim(batch: *mut sbn_batch) -> i32;
     pub fn sbn_proof_serialize(proof: *const sbn_proof, buf: *mut u8, len: *mut usize) -> i32;
     pub fn sbn_proof_timings(proof: *const sbn_proof, buf: *mut c_char, cap: usize) -> i32;
     pub fn sbn_proof_debug(proof: *const sbn_proof, which: i32, out: *mut u64, cap_words: usize, written: *mut usize) -> i32;

@@ -91,6 +91,7 @@ int sbn_ctx_synchronize(sbn_ctx* ctx);
 int sbn_ctx_select_field(sbn_ctx* ctx, uint64_t coset_shift);
 uint64_t sbn_ctx_launch_count(const sbn_ctx* ctx);  /* kernels launched so far through this context */
 uint64_t sbn_ctx_device_bytes(const sbn_ctx* ctx);  /* bytes held by the context's caching allocator */
+int sbn_ctx_trim(sbn_ctx* ctx);                     /* return the allocator's cached (unused) blocks to the device */
 /* Optional CUDA-event timing of the kernel families on the context's stream.  enable != 0 starts (and
  * resets) the collection; sbn_ctx_kernel_stats writes {"family":{"ms":total,"count":launch groups},...}. */
 int sbn_ctx_kernel_timing(sbn_ctx* ctx, int enable);
@@ -156,6 +157,7 @@ int sbn_prove_batch(sbn_batch* batch, int air, size_t num_io, const sbn_config* 
                     sbn_proof** proofs_out);
 uint64_t sbn_batch_launch_count(const sbn_batch* batch); /* kernels launched so far by all lanes */
 uint64_t sbn_batch_device_bytes(const sbn_batch* batch);  /* bytes held by the lanes' allocators */
+int sbn_batch_trim(sbn_batch* batch); /* return every lane's cached blocks to the device (e.g. before proving a different AIR) */
 
 /* Canonical little-endian wire format (DESIGN.md "Proof wire format").  Call with buf == NULL to get the length. */
 int sbn_proof_serialize(const sbn_proof* proof, uint8_t* buf, size_t* len);

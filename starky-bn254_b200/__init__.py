@@ -72,6 +72,8 @@ def lib():
         L.sbn_ctx_launch_count.argtypes = [vp]
         L.sbn_ctx_device_bytes.restype = C.c_uint64
         L.sbn_ctx_device_bytes.argtypes = [vp]
+        L.sbn_ctx_trim.argtypes = [vp]
+        L.sbn_batch_trim.argtypes = [vp]
         L.sbn_ctx_kernel_timing.argtypes = [vp, C.c_int]
         L.sbn_ctx_kernel_stats.argtypes = [vp, C.c_char_p, sz]
         L.sbn_config_standard_fast.argtypes = [vp]
@@ -136,6 +138,10 @@ class Context:
     @property
     def device_bytes(self):
         return int(lib().sbn_ctx_device_bytes(self.h))
+
+    def trim(self):
+        """Return the allocator's cached (unused) device blocks."""
+        self.check(lib().sbn_ctx_trim(self.h))
 
     def kernel_timing(self, enable=True):
         self.check(lib().sbn_ctx_kernel_timing(self.h, 1 if enable else 0))
@@ -380,6 +386,10 @@ class Batch:
     @property
     def device_bytes(self):
         return int(lib().sbn_batch_device_bytes(self.h))
+
+    def trim(self):
+        """Return every lane's cached device blocks (before switching to an AIR of another size)."""
+        lib().sbn_batch_trim(self.h)
 
     def close(self):
         if self.h:

@@ -154,6 +154,9 @@ struct sbn_ctx {
     for (auto& b : blocks) cudaFree(b.p);
     blocks.clear(); bytes_allocated = 0;
   }
+  void trim() {   // give the cached (unused) blocks back to the device; blocks in use stay
+    for (auto it = blocks.begin(); it != blocks.end();) { if (!it->used) { cudaFree(it->p); bytes_allocated -= it->bytes; it = blocks.erase(it); } else ++it; }
+  }
 };
 
 // RAII device buffer tied to the context's caching allocator.

@@ -20,40 +20,24 @@ static void launch_ext_powers(sbn_ctx* ctx, u64* out_a, u64* out_b, gl2 base, si
 }
 
 // ---- openings ----
-// One block per group of EVAL_COLS columns: every thread loads the four power-table entries of its index once and uses them for
-// all columns of the group (one block per column re-read the 4 x N table for each of the ~2 400 columns: 40 B of L1/L2 traffic
-// per 8 B of coefficients, the kernel ran at the L2 bandwidth).  Columns are read once, coalesced; sums are unreduced 160-bit
-// accumulators, folded once per thread, then a tree of exact field additions -- the same element whatever the grouping.
-#define EVAL_COLS 4
-__global__ void __launch_bounds__(256) k_eval_two_points(const u64* __restrict__ coeffs, size_t N, int ncols, const u64* __restrict__ pw /* [4][N]: z.a z.b zn.a zn.b */,
+// One block per column; reads the column once (coalesced), multiplies by the shared power tables.
+__global__ void __launch_bounds__(256) k_eval_two_points(const u64* __restrict__ coeffs, size_t N, const u64* __restrict__ pw /* [4][N]: z.a z.b zn.a zn.b */,
                                                          u64* __restrict__ out) {
-  const int c0 = blockIdx.x * EVAL_COLS;
-  gl_acc acc[EVAL_COLS][4];
-#pragma unroll
-  for (int c = 0; c < EVAL_COLS; c++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) acc[c][k] = gl_acc_zero();
+  const u64* col = coeffs + (size_t)blockIdx.x * N;
+  gl_acc a0 = gl_acc_zero(), a1 = gl_acc_zero(), a2 = gl_acc_zero(), a3 = gl_acc_zero();   // unreduced sums of products
   for (size_t j = threadIdx.x; j < N; j += blockDim.x) {
-    const u64 p0 = pw[j], p1 = pw[N + j], p2 = pw[2 * N + j], p3 = pw[3 * N + j];
-#pragma unroll
-    for (int c = 0; c < EVAL_COLS; c++) {
-      if (c0 + c < ncols) {   // uniform per block
-        const u64 v = coeffs[(size_t)(c0 + c) * N + j];
-        gl_acc_mac(acc[c][0], v, p0); gl_acc_mac(acc[c][1], v, p1); gl_acc_mac(acc[c][2], v, p2); gl_acc_mac(acc[c][3], v, p3);
-      }
-    }
+    u64 c = col[j];
+    gl_acc_mac(a0, c, pw[j]); gl_acc_mac(a1, c, pw[N + j]);
+    gl_acc_mac(a2, c, pw[2 * N + j]); gl_acc_mac(a3, c, pw[3 * N + j]);
   }
-  __shared__ u64 red[EVAL_COLS * 4][256];
-#pragma unroll
-  for (int c = 0; c < EVAL_COLS; c++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) red[c * 4 + k][threadIdx.x] = gl_acc_reduce(acc[c][k]);
+  __shared__ u64 red[4][256];
+  red[0][threadIdx.x] = gl_acc_reduce(a0); red[1][threadIdx.x] = gl_acc_reduce(a1); red[2][threadIdx.x] = gl_acc_reduce(a2); red[3][threadIdx.x] = gl_acc_reduce(a3);
   __syncthreads();
   for (int d = 128; d > 0; d >>= 1) {
-    if ((int)threadIdx.x < d) for (int k = 0; k < EVAL_COLS * 4; k++) red[k][threadIdx.x] = gl_add(red[k][threadIdx.x], red[k][threadIdx.x + d]);
+    if ((int)threadIdx.x < d) for (int k = 0; k < 4; k++) red[k][threadIdx.x] = gl_add(red[k][threadIdx.x], red[k][threadIdx.x + d]);
     __syncthreads();
   }
-  if (threadIdx.x < EVAL_COLS * 4 && c0 + (int)(threadIdx.x >> 2) < ncols) out[(size_t)c0 * 4 + threadIdx.x] = red[threadIdx.x][0];
+  if (threadIdx.x < 4) out[(size_t)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
 }
 
 DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1) {
@@ -67,7 +51,7 @@ DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1) {
 void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, const u64* pw, u64* d_out) {
   if (ncols <= 0) return;
   KScope ks(ctx, "openings_eval");
-  k_eval_two_points<<<(ncols + EVAL_COLS - 1) / EVAL_COLS, 256, 0, ctx->stream>>>(coeffs, size_t(1) << logn, ncols, pw, d_out);
+  k_eval_two_points<<<ncols, 256, 0, ctx->stream>>>(coeffs, size_t(1) << logn, pw, d_out);
   LAUNCH_CHECK(ctx);
 }
 void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, gl2 zeta, gl2 zeta_next, u64* d_out) {

@@ -40,6 +40,7 @@ struct PhaseTimer {  // CUDA-event timings of the prover phases (names follow pl
   sbn_ctx* ctx; std::vector<std::pair<std::string, cudaEvent_t>> ev;
   explicit PhaseTimer(sbn_ctx* c) : ctx(c) { mark("start"); }
   void mark(const char* name) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); ev.push_back({name, e}); }
+  ~PhaseTimer() { for (auto& e : ev) cudaEventDestroy(e.second); }   // an exception between marks must not leak the events
   std::string json() {
     cudaEventSynchronize(ev.back().second);
     std::ostringstream os; os << "{";
@@ -721,6 +722,13 @@ void sbn_batch_destroy(sbn_batch* b) {
   delete b;
 }
 const char* sbn_batch_last_error(const sbn_batch* b) { return b ? b->last_error.c_str() : g_create_error.c_str(); }
+int sbn_ctx_trim(sbn_ctx* ctx) { API_BEGIN SBN_REQUIRE(ctx, "null context"); CUDA_CHECK(cudaSetDevice(ctx->device)); ctx->sync(); ctx->trim(); API_END(ctx) }
+int sbn_batch_trim(sbn_batch* b) {
+  if (!b) return SBN_ERR_INVALID;
+  cudaSetDevice(b->device);
+  for (auto* c : b->lanes) { cudaStreamSynchronize(c->stream); c->trim(); }
+  return 0;
+}
 uint64_t sbn_batch_launch_count(const sbn_batch* b) { uint64_t n = 0; if (b) for (auto* c : b->lanes) n += c->launches; return n; }
 uint64_t sbn_batch_device_bytes(const sbn_batch* b) { uint64_t n = 0; if (b) for (auto* c : b->lanes) n += c->bytes_allocated; return n; }
 

@@ -93,6 +93,24 @@ def main():
         out[name] = {"ios_sha256": sha(ios), "trace_sha256": sha(trace.tobytes()), "proof_sha256": sha(proof), "proof_len": len(proof),
                      "trace_cap0": ["%016x" % int.from_bytes(proof[4 + 8 * i:12 + 8 * i], "little") for i in range(4)]}
         print(name, out[name], flush=True)
+    # BASELINE.json configs[4] at 2^16 rows, rate_bits 1..3 (the sweep's own numpy-generated inputs; ~4 minutes of oracle time)
+    if "--with-sweep" in sys.argv:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sweep_modular
+        n = 1 << 16
+        ios = sweep_modular.fast_ios(n)
+        air = orc.Air(orc.AIR_MODULAR, n)
+        trace, _ = air.generate_trace(ios)
+        blk = {"ios_sha256": sha(ios), "trace_sha256": sha(trace.tobytes())}
+        for r in (1, 2, 3):
+            cfg = orc.Config.standard_fast_config(rate_bits=r)
+            proof = air.prove(trace, np.zeros(0, dtype=np.uint64), cfg)
+            assert air.verify(proof, cfg)[0]
+            blk["rate_bits_%d" % r] = {"proof_sha256": sha(proof), "proof_len": len(proof),
+                                       "trace_cap0": ["%016x" % int.from_bytes(proof[4 + 8 * i:12 + 8 * i], "little") for i in range(4)]}
+        out["modular_2p16_sweep"] = blk
+    else:
+        out["modular_2p16_sweep"] = json.load(open(os.path.join(HERE, "golden.json")))["modular_2p16_sweep"]
     json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 

@@ -531,3 +531,59 @@ def test_uncertainty_switches_match_oracle(ctx, sbn, orc, coset_shift, hack):
             sbn.prove(stark, bad, t2, pi)
         finally:
             t2.free()
+
+
+def test_modular_sweep_2p16_matches_oracle_goldens(ctx, sbn, golden):
+    """BASELINE.json configs[4] at its smallest size: ModularStark with 2^16 rows (the sweep's own inputs), rate_bits 1 / 2 / 3.
+    Trace and proof digests come from the CPU oracle (tests/golden/golden.json, `modular_2p16_sweep`: 30 / 63 / 134 s of oracle
+    time, so they are committed rather than recomputed); the same inputs streamed (SBN_STREAMING=1) must give the same bytes."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import sweep_modular
+    g = golden["modular_2p16_sweep"]
+    n = 1 << 16
+    ios = sweep_modular.fast_ios(n)
+    assert hashlib.sha256(ios).hexdigest() == g["ios_sha256"]
+    stark = sbn.ModularStark(n, ctx)
+    tr = stark.generate_trace(ios)
+    assert hashlib.sha256(tr.download().tobytes()).hexdigest() == g["trace_sha256"]
+    for r in (1, 2, 3):
+        cfg = stark.config(); cfg.rate_bits = r
+        pb = sbn.prove(stark, cfg, tr, np.zeros(0, dtype=np.uint64)).to_bytes()
+        want = g["rate_bits_%d" % r]
+        assert len(pb) == want["proof_len"]
+        assert ["%016x" % int.from_bytes(pb[4 + 8 * i:12 + 8 * i], "little") for i in range(4)] == want["trace_cap0"]
+        assert hashlib.sha256(pb).hexdigest() == want["proof_sha256"], r
+    os.environ["SBN_STREAMING"] = "1"
+    try:
+        cfg = stark.config(); cfg.rate_bits = 2
+        assert hashlib.sha256(sbn.prove(stark, cfg, tr, np.zeros(0, dtype=np.uint64)).to_bytes()).hexdigest() == g["rate_bits_2"]["proof_sha256"]
+    finally:
+        del os.environ["SBN_STREAMING"]
+        tr.free()
+
+
+def test_two_contexts_on_two_devices_in_one_process(sbn, golden):
+    """Per-device function attributes (NTT shared-memory opt-in) and device binding of every entry point: a context on GPU 1 created
+    after one on GPU 0 must prove the same bytes (round-1 advisory: a process-wide flag left the second device without the opt-in)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    proofs = []
+    ctxs = [sbn.Context(0), sbn.Context(1)]
+    try:
+        for c in ctxs:
+            stark = sbn.ModularStark(4096, c)     # 2^12 rows: the two-pass NTT with its large dynamic shared memory
+            tr = stark.generate_trace(sbn.synthetic.modular_ios(4096))
+            proofs.append(sbn.prove(stark, stark.config(), tr, np.zeros(0, dtype=np.uint64)).to_bytes())
+            tr.free()
+        # interleaved use of the two contexts from one thread
+        tr0 = sbn.ModularStark(512, ctxs[0]).generate_trace(sbn.synthetic.modular_ios(512))
+        tr1 = sbn.ModularStark(512, ctxs[1]).generate_trace(sbn.synthetic.modular_ios(512))
+        assert (tr0.download() == tr1.download()).all()
+        tr0.free(); tr1.free()
+    finally:
+        for c in ctxs:
+            c.close()
+    assert proofs[0] == proofs[1]
