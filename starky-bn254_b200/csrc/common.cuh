@@ -8,6 +8,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <chrono>
 #include <thread>
 #include <tuple>
 #include <string>
@@ -71,15 +72,17 @@ struct sbn_ctx {
   unsigned ntt_attr_mask = 0;                      // sub-transform sizes whose kernels already have their shared-memory opt-in on this device
   int live_handles = 0;                            // sbn_trace objects still holding buffers of this context
   bool destroy_pending = false;                    // sbn_ctx_destroy was called with live handles: the last sbn_trace_free destroys
-  // Host waits poll the stream and yield the core between polls: as responsive as a spin wait when cores are free (a blocking
-  // event wait measured ~1 ms per wake-up on the bench box: 170 vs 87 ms for one G1 proof), but a batch's lanes (one host thread
-  // each) and the eight ranks of a box share the cores instead of spinning against each other.
+  // Host waits: poll the stream, yielding the core between polls, and after ~300 polls (a few hundred microseconds: longer than
+  // the short kernels most waits are for) sleep between polls, 20 us growing to 100 us.  A blocking event wait measured ~1 ms per
+  // wake-up on the bench box (170 vs 87 ms for one G1 proof); a pure spin / yield loop keeps one core per lane busy while a 25 ms
+  // leaf-hash kernel runs, and eight ranks x six lanes on a 32-core box then slow each other down (8-GPU step 66.3 vs 63.2 ms).
   void sync() {
-    for (;;) {
+    for (int polls = 0;; polls++) {
       cudaError_t e = cudaStreamQuery(stream);
       if (e == cudaSuccess) return;
       if (e != cudaErrorNotReady) throw SbnError(-2, std::string("stream synchronisation: ") + cudaGetErrorString(e));
-      std::this_thread::yield();
+      if (polls < 300) std::this_thread::yield();
+      else std::this_thread::sleep_for(std::chrono::microseconds(polls < 600 ? 20 : 100));
     }
   }
   // Small host -> device uploads (challenge-dependent tables, descriptors) go through a pinned bump arena: a cudaMemcpyAsync from
