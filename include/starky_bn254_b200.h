@@ -142,7 +142,8 @@ int sbn_prove_sharded(sbn_ctx* ctx, const sbn_config* config, const sbn_trace* t
  * A batch owns `lanes` worker contexts on one GPU (one CUDA stream, one device allocator and one host thread each) that share
  * one set of read-only device tables; proofs are handed to the lanes as they become free, so the serial sections of one proof
  * (exponentiation chains, lookup walk, host-side Fiat-Shamir) overlap with the wide kernels of the others, and the kernels of
- * small traces (Fq12: 2^14 leaves) run concurrently.  Every proof is byte-identical to the one sbn_prove returns for the same
+ * small traces (Fq12: 2^14 leaves) run concurrently; fewer lanes run at once when the proofs' footprint (trace + coefficients +
+ * LDE) would not fit the device that many times.  Every proof is byte-identical to the one sbn_prove returns for the same
  * inputs.  ios[j] points to the num_io input records of proof j (host memory, or device memory with SBN_BATCH_IOS_ON_DEVICE).
  * SBN_BATCH_FILL_OUTPUTS: the `output` field of every record is taken from the trace (the chain result, sbn_trace_results)
  * instead of being read from the caller's record -- the caller then need not compute the BN254 results natively first.

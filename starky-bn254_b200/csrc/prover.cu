@@ -13,6 +13,7 @@
 #include "tracegen.cuh"
 #include "poseidon.cuh"
 #include <atomic>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -786,7 +787,18 @@ int sbn_prove_batch(sbn_batch* b, int air_id, size_t num_io, const sbn_config* c
       } catch (const SbnError& e) { failed = true; std::lock_guard<std::mutex> g(err_mu); if (!err_code) { err_code = e.code; err = e.what(); } }
       catch (const std::exception& e) { failed = true; std::lock_guard<std::mutex> g(err_mu); if (!err_code) { err_code = SBN_ERR_INTERNAL; err = e.what(); } }
     };
-    const size_t nworkers = std::min(b->lanes.size(), count);
+    // lanes that may run at once: each proof in flight holds trace + coefficients + LDE of the trace and Z batches (+ Z values);
+    // large shapes (G1 with 512 instances: 2^18 rows; Fq12 with 128: 10 250 columns x 2^16 rows) do not fit six times
+    size_t nworkers = std::min(b->lanes.size(), count);
+    {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+        const double nz = air.perm_pairs.empty() ? 0.0 : (double)((air.perm_pairs.size() * config->num_challenges + 1) / 2);
+        const double per_proof = 8.0 * (double)air.num_rows * (((double)air.num_columns + nz) * (2.0 + (double)(1u << config->rate_bits)) + (double)air.num_columns) * 1.15;
+        const size_t fit = (size_t)std::max(1.0, std::floor(0.8 * (double)total_b / per_proof));
+        nworkers = std::min(nworkers, fit);
+      }
+    }
     std::vector<std::thread> threads;
     for (size_t w = 1; w < nworkers; w++) threads.emplace_back(work, b->lanes[w]);
     if (nworkers) work(b->lanes[0]);   // the calling thread drives lane 0
