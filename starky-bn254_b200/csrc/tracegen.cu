@@ -175,6 +175,217 @@ __global__ void __launch_bounds__(32) k_lookup_walk_chunked(const u32* __restric
   }
 }
 
+// Same result without the walk: one block per lookup, u16 table (R = 65 536).  With delta(v) = +1 for an absent value (a push),
+// -(c - 1) for a value with c >= 2 copies (its pops) and S the prefix sums of delta, M = min(0, running minimum of S):
+//   stack height after v  H(v) = S(v) - M(v),   positions deferred so far  D(v) = -M(v),
+//   a pushed value u is popped by the first w > u with H(w) < H(u), as pop number H(w-1) - H(u) of that group; a push nobody
+//   pops is entry H(u) - 1 of the leftover stack; the group at v pops min(c - 1, H(v-1)) values and defers the rest, whose
+//   k-th overall takes leftover[k] (or R-1 past the leftover's end)  -- the pairing lookup.rs:60-111 produces with its
+//   explicit stack.  Passes 1-2 are two block scans with 64 consecutive values per thread (heights into shared memory under a
+//   4-ary minimum tree for the "next smaller" search; offsets and deferred counts into the scratch); passes 3-4 place every
+//   table value independently, a warp taking 32 consecutive values per step so that its stores fall into one short run of
+//   rows.  65 536 dependent steps of one warp become 64 per thread.
+constexpr int LWP_THREADS = 1024, LWP_R = 1 << 16, LWP_VPT = LWP_R / LWP_THREADS, LWP_TREE = 21844, LWP_HUGE = 32, LWP_HUGE_MIN = 2048;
+struct LwpScan { int sum, mn; u32 off; };
+constexpr size_t LWP_SMEM = (size_t)LWP_R * 2 + (size_t)LWP_TREE * 2 + 32 * sizeof(LwpScan) + (2 + LWP_HUGE) * 4;
+// level l >= 1 of the minimum tree (65536 >> 2l nodes, node i = min of nodes 4i .. 4i+3 one level down) starts at LWP_OFF[l]; level 0 = heights
+__constant__ int LWP_OFF[8] = {0, 0, 16384, 20480, 21504, 21760, 21824, 21840};
+// heights are stored at a swizzled index: bank-conflict free both for "64 consecutive values per lane" and "32 consecutive values per warp"
+__device__ __forceinline__ u32 lwp_swz(u32 v) { return v ^ ((v >> 5) & 0x3eu); }
+// First w > u with H(w) < x, or -1: up the tree past the siblings to the right, down into the first subtree whose minimum is below x.
+// One node per iteration and a warp-wide vote as the loop condition, so the 32 searches of a warp advance together (with early
+// returns the lanes leave the loops at different times and each finishes its search alone: measured 1.95 active lanes per
+// instruction).  Every lane of the warp calls it; `active` = this lane searches.
+__device__ __forceinline__ int lwp_next_smaller(const u16* H, const u16* tree, int u, u32 x, bool active) {
+  int pos = u + 1, l = 0, res = -1;
+  bool asc = true, run = active;
+  while (__any_sync(0xffffffffu, run)) {
+    if (run && asc) {   // a node that is the first child of its parent: the parent stands for it and its three siblings
+      int k = (__ffs(pos) - 1) >> 1;
+      k = min(k, 7 - l);
+      pos >>= 2 * k; l += k;
+      if ((pos & 3) == 0) run = false;   // level 7, node 4: past the end -- nobody pops u
+    }
+    if (run) {
+      const u32 t = l == 0 ? (u32)H[lwp_swz((u32)pos)] : (u32)tree[LWP_OFF[l] + pos];
+      if (t < x) { if (l == 0) { res = pos; run = false; } else { l--; pos <<= 2; asc = false; } }
+      else pos++;
+    }
+  }
+  return res;
+}
+__global__ void __launch_bounds__(LWP_THREADS, 1) k_lookup_walk_parallel(const u32* __restrict__ cnt_all, size_t N, u64* __restrict__ cols, const LookupDesc* __restrict__ descs,
+                                                                         u32* __restrict__ stack_all, u32* __restrict__ scratch_all) {
+  extern __shared__ __align__(16) unsigned char lwp_smem[];
+  u16* H = reinterpret_cast<u16*>(lwp_smem);
+  u16* tree = H + LWP_R;
+  LwpScan* wscan = reinterpret_cast<LwpScan*>(tree + LWP_TREE);
+  u32* misc = reinterpret_cast<u32*>(wscan + 32);            // [0] positions deferred before the table's last value, [1] length of huge[]
+  u32* huge = misc + 2;                                       // values with more than LWP_HUGE_MIN copies: written by the whole block
+  constexpr u32 R = LWP_R, FULL = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const LookupDesc d = descs[blockIdx.x];
+  const u32* cnt = cnt_all + (size_t)blockIdx.x * R;
+  u32* leftover = stack_all + (size_t)blockIdx.x * R;
+  u32* off0g = scratch_all + (size_t)blockIdx.x * 2 * R;     // exclusive prefix sums of the counts
+  u32* dg = off0g + R;                                        // D(v)
+  u64* sorted = cols + (size_t)d.sorted_col * N;
+  u64* perm = cols + (size_t)d.perm_col * N;
+  const u32 v0 = (u32)tid * LWP_VPT;
+  const uint4* c4 = reinterpret_cast<const uint4*>(cnt + v0);
+  if (tid == 0) misc[1] = 0;
+  // ---- pass 1: per-thread totals, block scan ----
+  LwpScan mine; mine.sum = 0; mine.mn = 0x3fffffff; mine.off = 0;
+#pragma unroll 1
+  for (int q = 0; q < LWP_VPT / 4; q++) {
+    const uint4 x = c4[q];
+    const u32 cc[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 c = cc[k], v = v0 + q * 4 + k;
+      if (v != R - 1) mine.sum += c == 0 ? 1 : -(int)(c - 1);
+      mine.mn = min(mine.mn, mine.sum);
+      mine.off += c;
+    }
+  }
+  LwpScan inc = mine;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const int ps = __shfl_up_sync(FULL, inc.sum, dd), pm = __shfl_up_sync(FULL, inc.mn, dd);
+    const u32 po = __shfl_up_sync(FULL, inc.off, dd);
+    if (lane >= dd) { inc.mn = min(pm, ps + inc.mn); inc.sum += ps; inc.off += po; }
+  }
+  if (lane == 31) wscan[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    LwpScan w = wscan[lane];
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const int ps = __shfl_up_sync(FULL, w.sum, dd), pm = __shfl_up_sync(FULL, w.mn, dd);
+      const u32 po = __shfl_up_sync(FULL, w.off, dd);
+      if (lane >= dd) { w.mn = min(pm, ps + w.mn); w.sum += ps; w.off += po; }
+    }
+    wscan[lane] = w;   // inclusive over warps
+  }
+  __syncthreads();
+  LwpScan base;        // everything before this thread's first value
+  {
+    LwpScan ex;
+    ex.sum = __shfl_up_sync(FULL, inc.sum, 1); ex.mn = __shfl_up_sync(FULL, inc.mn, 1); ex.off = __shfl_up_sync(FULL, inc.off, 1);
+    if (lane == 0) { ex.sum = 0; ex.mn = 0x3fffffff; ex.off = 0; }
+    if (warp == 0) base = ex;
+    else { const LwpScan wb = wscan[warp - 1]; base.sum = wb.sum + ex.sum; base.mn = min(wb.mn, wb.sum + ex.mn); base.off = wb.off + ex.off; }
+  }
+  // ---- pass 2: heights, the three lowest tree levels, offsets and deferred counts ----
+  {
+    int S = base.sum, M = min(0, base.mn); u32 off = base.off, m1 = 0xffffu, m2 = 0xffffu, m3 = 0xffffu;
+#pragma unroll 1
+    for (int q = 0; q < LWP_VPT / 4; q++) {
+      const uint4 x = c4[q];
+      const u32 cc[4] = {x.x, x.y, x.z, x.w};
+      uint4 o, dq;
+      u32* op = reinterpret_cast<u32*>(&o);
+      u32* dp = reinterpret_cast<u32*>(&dq);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const u32 c = cc[k], v = v0 + q * 4 + k;
+        if (v != R - 1) S += c == 0 ? 1 : -(int)(c - 1);
+        M = min(M, S);
+        const u32 h = (u32)(S - M);
+        H[lwp_swz(v)] = (u16)h;
+        m1 = min(m1, h);
+        op[k] = off; off += c;
+        dp[k] = (u32)(-M);
+      }
+      reinterpret_cast<uint4*>(off0g + v0)[q] = o;
+      reinterpret_cast<uint4*>(dg + v0)[q] = dq;
+      tree[(v0 >> 2) + q] = (u16)m1;
+      m2 = min(m2, m1); m1 = 0xffffu;
+      if ((q & 3) == 3) { tree[16384 + (v0 >> 4) + (q >> 2)] = (u16)m2; m3 = min(m3, m2); m2 = 0xffffu; }
+    }
+    tree[20480 + tid] = (u16)m3;
+    if (tid == LWP_THREADS - 1) misc[0] = (u32)(-M);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int l = 4; l <= 7; l++) {   // 256, 64, 16, 4 nodes
+    const int n = LWP_R >> (2 * l);
+    if (tid < n) { const u16* c = tree + LWP_OFF[l - 1] + 4 * tid; tree[LWP_OFF[l] + tid] = min(min(c[0], c[1]), min(c[2], c[3])); }
+    __syncthreads();
+  }
+  const u32 top = H[lwp_swz(R - 1)];
+  const u32 wbase = (u32)warp * (R / 32);
+  // ---- pass 3: every push finds its place; first copies and sorted runs ----
+  bool any_deferred = false;
+#pragma unroll 1
+  for (int j = 0; j < (int)(R / 32 / 32); j++) {
+    const u32 v = wbase + j * 32 + lane;
+    const u32 c = cnt[v], off = off0g[v];
+    const bool live = v != R - 1, push = live && c == 0;
+    const u32 hx = H[lwp_swz(v)];
+    const int w = lwp_next_smaller(H, tree, (int)v, hx, push);
+    if (push) {
+      if (w < 0) leftover[hx - 1] = v;
+      else perm[off0g[w] + 1 + ((u32)H[lwp_swz((u32)w - 1)] - hx)] = v;
+    } else if (live) {
+      perm[off] = v;
+      if (c <= 32) for (u32 t = 0; t < c; t++) sorted[off + t] = v;
+      const u32 hp = v ? (u32)H[lwp_swz(v - 1)] : 0u;
+      if (c - 1 > hp) any_deferred = true;
+      if (c > LWP_HUGE_MIN) { const u32 slot = atomicAdd(&misc[1], 1u); if (slot < LWP_HUGE) huge[slot] = v; }
+    }
+    u32 big = __ballot_sync(FULL, live && c > 32 && c <= LWP_HUGE_MIN);
+    while (big) {
+      const int i = __ffs(big) - 1;
+      big &= big - 1;
+      const u32 ci = __shfl_sync(FULL, c, i), oi = __shfl_sync(FULL, off, i), vi = wbase + j * 32 + i;
+      for (u32 t = lane; t < ci; t += 32) sorted[oi + t] = vi;
+    }
+  }
+  any_deferred = __syncthreads_or(any_deferred);   // leftover[] and huge[] complete
+  const u32 nhuge = misc[1];                        // > LWP_HUGE: the list overflowed, the values beyond it are written by their warps
+  // ---- pass 4: deferred positions take the leftover stack bottom-first, then the table's last value ----
+#pragma unroll 1
+  for (int j = 0; j < (int)(R / 32 / 32); j++) {
+    if (!any_deferred && nhuge <= LWP_HUGE) break;
+    const u32 v = wbase + j * 32 + lane;
+    const u32 c = cnt[v];
+    const bool live = v != R - 1;
+    const u32 hp = v ? (u32)H[lwp_swz(v - 1)] : 0u;
+    bool listed = false;
+    if (live && c > LWP_HUGE_MIN) for (u32 e = 0; e < min(nhuge, (u32)LWP_HUGE); e++) listed |= huge[e] == v;
+    const u32 nd = (live && !listed && c >= 2 && c - 1 > hp) ? c - 1 - hp : 0u;
+    const bool fill = live && !listed && c > LWP_HUGE_MIN;   // a long run that did not fit the list
+    if (!__ballot_sync(FULL, nd > 0 || fill)) continue;
+    const u32 off = off0g[v], pos = off + 1 + hp, D = v ? dg[v - 1] : 0u;
+    if (nd <= 32) for (u32 t = 0; t < nd; t++) { const u32 k = D + t; perm[pos + t] = k < top ? leftover[k] : R - 1; }
+    u32 big = __ballot_sync(FULL, nd > 32 || fill);
+    while (big) {
+      const int i = __ffs(big) - 1;
+      big &= big - 1;
+      const u32 ni = __shfl_sync(FULL, nd, i), pi = __shfl_sync(FULL, pos, i), Di = __shfl_sync(FULL, D, i);
+      if (ni > 32) for (u32 t = lane; t < ni; t += 32) { const u32 k = Di + t; perm[pi + t] = k < top ? leftover[k] : R - 1; }
+      if (__shfl_sync(FULL, (int)fill, i)) {
+        const u32 ci = __shfl_sync(FULL, c, i), oi = __shfl_sync(FULL, off, i), vi = wbase + j * 32 + i;
+        for (u32 t = lane; t < ci; t += 32) sorted[oi + t] = vi;
+      }
+    }
+  }
+  for (u32 e = 0; e < min(nhuge, (u32)LWP_HUGE); e++) {   // the longest runs: sorted copies and deferred positions by the whole block
+    const u32 v = huge[e], c = cnt[v], off = off0g[v], hp = v ? (u32)H[lwp_swz(v - 1)] : 0u, D = v ? dg[v - 1] : 0u;
+    const u32 npop = min(c - 1, hp), nd = c - 1 - npop;
+    for (u32 t = tid; t < c; t += LWP_THREADS) sorted[off + t] = v;
+    for (u32 t = tid; t < nd; t += LWP_THREADS) { const u32 k = D + t; perm[off + 1 + npop + t] = k < top ? leftover[k] : R - 1; }
+  }
+  {  // the table's last value R-1 occurs tcount times: its surplus inputs are deferred, never popped
+    const size_t c = cnt[R - 1], tcount = N - R + 1, m = c < tcount ? c : tcount, lo = off0g[R - 1];
+    const u32 D = misc[0];
+    for (size_t t = tid; t < c; t += LWP_THREADS) sorted[lo + t] = R - 1;
+    for (size_t t = tid; t < m; t += LWP_THREADS) perm[lo + t] = R - 1;
+    if (c > tcount) for (size_t t = tid; t < c - tcount; t += LWP_THREADS) { const size_t k = D + t; perm[lo + tcount + t] = k < top ? leftover[k] : R - 1; }
+  }
+}
+
 static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::vector<LookupDesc>& descs) {
   SBN_REQUIRE(N >= R, "range-check table does not fit the trace (reference asserts rows >= range_max)");
   SBN_REQUIRE(N < (size_t(1) << 32), "trace too long");
@@ -189,7 +400,11 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
   ctx->upload(d_desc, descs.data(), descs.size() * sizeof(LookupDesc));
   // SBN_LOOKUP_SEQUENTIAL=1 selects the one-value-per-step kernel (k_lookup_walk), kept as the in-library cross-check of the
   // chunked kernel (tests/test_gpu_parity.py compares the two on skewed and uniform columns).
+  // SBN_LOOKUP_WALK=chunked selects the one-warp-per-lookup kernel for the u16 table too (it always serves the other table sizes).
   const bool sequential = getenv("SBN_LOOKUP_SEQUENTIAL") != nullptr;
+  const char* walk_env = getenv("SBN_LOOKUP_WALK");
+  const bool parallel = !sequential && R == (u32)LWP_R && N < (size_t(1) << 31) && !(walk_env && !strcmp(walk_env, "chunked"));
+  if (parallel) CUDA_CHECK(cudaFuncSetAttribute(k_lookup_walk_parallel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LWP_SMEM));
   if (sequential) group = std::min(group, std::max<size_t>(1, (size_t(512) << 20) / ((N + 2 * (size_t)R) * 4)));
   DevBuf<u32> cnt(ctx, group * R), stack(ctx, group * R);
   DevBuf<uint2> defer(ctx, sequential ? 1 : group * R);
@@ -203,6 +418,7 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
     LAUNCH_CHECK(ctx); }
     KScope ks2(ctx, "lookup_walk");
     if (sequential) k_lookup_walk<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer_seq);
+    else if (parallel) k_lookup_walk_parallel<<<(unsigned)ng, LWP_THREADS, LWP_SMEM, ctx->stream>>>(cnt, N, d_cols, d_desc + g0, stack, reinterpret_cast<u32*>((uint2*)defer));
     else k_lookup_walk_chunked<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer);
     LAUNCH_CHECK(ctx);
   }

@@ -131,6 +131,30 @@ def test_lookup_kernels_agree(ctx, sbn, monkeypatch):
     assert (a == b).all()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["uniform", "one_instance_repeated", "two_instances", "rows_2p17"])
+def test_parallel_lookup_walk_matches_walk_kernels(ctx, sbn, monkeypatch, case):
+    """u16 table: the scan-based kernel (one block per lookup, every table value placed independently) against the chunked and
+    the one-value-per-step walks, on uniform limbs, on columns with long runs and many deferred positions (one / two distinct
+    instances repeated: every value occurs 128 / 64 times) and with more rows than table values (2^17 rows)."""
+    n = 256 if case == "rows_2p17" else 128
+    ios = sbn.synthetic.g1_exp_ios(n, seed=77)
+    size = len(ios) // n
+    if case == "one_instance_repeated":
+        ios = ios[:size] * n
+    elif case == "two_instances":
+        ios = (ios[:size] + ios[size:2 * size]) * (n // 2)
+    g1 = sbn.G1ExpStark(n, ctx)
+    a = g1.generate_trace(ios).download()
+    monkeypatch.setenv("SBN_LOOKUP_WALK", "chunked")
+    b = g1.generate_trace(ios).download()
+    assert (a == b).all()
+    if case != "rows_2p17":
+        monkeypatch.setenv("SBN_LOOKUP_SEQUENTIAL", "1")
+        c = g1.generate_trace(ios).download()
+        assert (a == c).all()
+
+
 def test_modular_proof_matches_oracle_bytes(ctx, sbn, orc, golden, monkeypatch):
     monkeypatch.setenv("SBN_DEBUG_INTERMEDIATES", "1")
     n = 512
