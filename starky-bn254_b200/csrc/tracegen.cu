@@ -196,20 +196,20 @@ __device__ __forceinline__ u32 lwp_swz(u32 v) { return v ^ ((v >> 5) & 0x3eu); }
 // One node per iteration and a warp-wide vote as the loop condition, so the 32 searches of a warp advance together (with early
 // returns the lanes leave the loops at different times and each finishes its search alone: measured 1.95 active lanes per
 // instruction).  Every lane of the warp calls it; `active` = this lane searches.
-__device__ __forceinline__ int lwp_next_smaller(const u16* H, const u16* tree, int u, u32 x, bool active) {
+__device__ __forceinline__ int lwp_next_smaller(const u16* H, int u, u32 x, bool active) {
   int pos = u + 1, l = 0, res = -1;
-  bool asc = true, run = active;
-  while (__any_sync(0xffffffffu, run)) {
-    if (run && asc) {   // a node that is the first child of its parent: the parent stands for it and its three siblings
-      int k = (__ffs(pos) - 1) >> 1;
-      k = min(k, 7 - l);
+  int mode = active ? 1 : 0;   // 0 finished, 1 going up, 2 going down
+  while (__any_sync(0xffffffffu, mode != 0)) {
+    if (mode == 1) {   // a node that is the first child of its parent: the parent stands for it and its three siblings
+      const int k = min((__ffs(pos) - 1) >> 1, 7 - l);
       pos >>= 2 * k; l += k;
-      if ((pos & 3) == 0) run = false;   // level 7, node 4: past the end -- nobody pops u
+      if ((pos & 3) == 0) mode = 0;   // level 7, node 4: past the end -- nobody pops u
     }
-    if (run) {
-      const u32 t = l == 0 ? (u32)H[lwp_swz((u32)pos)] : (u32)tree[LWP_OFF[l] + pos];
-      if (t < x) { if (l == 0) { res = pos; run = false; } else { l--; pos <<= 2; asc = false; } }
-      else pos++;
+    if (mode != 0) {
+      const u32 t = H[(l == 0 ? 0 : LWP_R + LWP_OFF[l]) + (pos ^ (l == 0 ? (pos >> 5) & 0x3e : 0))];   // the tree follows the heights in shared memory
+      if (t >= x) pos++;
+      else if (l == 0) { res = pos; mode = 0; }
+      else { l--; pos <<= 2; mode = 2; }
     }
   }
   return res;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(LWP_THREADS, 1) k_lookup_walk_parallel(const u
     const u32 c = cnt[v], off = off0g[v];
     const bool live = v != R - 1, push = live && c == 0;
     const u32 hx = H[lwp_swz(v)];
-    const int w = lwp_next_smaller(H, tree, (int)v, hx, push);
+    const int w = lwp_next_smaller(H, (int)v, hx, push);
     if (push) {
       if (w < 0) leftover[hx - 1] = v;
       else perm[off0g[w] + 1 + ((u32)H[lwp_swz((u32)w - 1)] - hx)] = v;
@@ -504,9 +504,17 @@ __global__ void __launch_bounds__(128) k_g1_affine(const G1Jac* __restrict__ jac
 #pragma unroll
   for (int k = 0; k < 8; k++) aff[i * 16 + 8 + k] = w[k];
 }
+// Rows of the exponentiation AIRs alternate between the squaring / doubling step (even rows) and the conditional multiplication /
+// addition step (odd rows).  A warp takes 32 rows of one parity (warp 2g: rows 64g, 64g+2, ...; warp 2g+1: the odd ones) so that
+// its lanes run the same witness code: with 32 consecutive rows per warp the two operations were serialised (measured 12.1
+// active lanes per instruction in k_g1_rows).  The two warps of a pair sit in the same block and fill each other's sectors.
+__device__ __forceinline__ size_t exp_row_of_thread() {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  return ((t >> 6) << 6) + 2 * (t & 31) + ((t >> 5) & 1);
+}
 // main columns: a(32) b(32) G1Output(320) flags(14)   (reference src/curves/g1/exp.rs:165-230, flags.rs:46-134)
 __global__ void __launch_bounds__(128) k_g1_rows(const G1Io* __restrict__ ios, const u32* __restrict__ aff, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
-  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t r = exp_row_of_thread();
   if (r >= N) return;
   const size_t inst = r >> 9; const int rr = (int)(r & 511), k = rr >> 1;
   u32 e[8];
@@ -644,7 +652,7 @@ __global__ void __launch_bounds__(32) k_fq_chain(const sbn_fq_exp_io* __restrict
 }
 // main columns: a16 b16 FqOutput(112) flags14   (reference src/fields/fq/exp.rs:128-178)
 __global__ void __launch_bounds__(128) k_fq_rows(const sbn_fq_exp_io* __restrict__ ios, const u32* __restrict__ chain, u64* __restrict__ cols, size_t N) {
-  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t r = exp_row_of_thread();
   if (r >= N) return;
   const size_t inst = r >> 9; const int rr = (int)(r & 511), k = rr >> 1;
   u32 e[8];
@@ -720,7 +728,7 @@ __global__ void __launch_bounds__(128) k_g2_affine(const G2Jac* __restrict__ jac
 }
 // main columns: a(64) b(64) G2Output(640) flags(14)   (reference src/curves/g2/exp.rs:180-245)
 __global__ void __launch_bounds__(128) k_g2_rows(const sbn_g2_exp_io* __restrict__ ios, const u32* __restrict__ aff, u64* __restrict__ cols, size_t N, int* __restrict__ err) {
-  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t r = exp_row_of_thread();
   if (r >= N) return;
   const size_t inst = r >> 9; const int rr = (int)(r & 511), k = rr >> 1;
   u32 e[8];
