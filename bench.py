@@ -35,6 +35,9 @@ AIRS = {
     "fq": ("FqExpStark", 1, 128, "fq_exp_ios", "Fq-exp STARK proofs/sec",
            "FqExpStark num_io=128: 128 independent BN254 Fq exponentiations per proof, 2^16 rows x 960 columns, StarkConfig::standard_fast_config"),
 }
+# lanes per batch (gpurun_out/r2w_*: Fq12 6 / 10 / 16 / 24 lanes -> 13.5 / 13.3 / 14.3 / 13.8 proofs/s device-resident, 12.8 / 13.9 / 14.8 / 16.0 end to end;
+# Fq 6 / 8 / 12 -> 30.5 / 32.9 / 31.8; G2 6 / 8 -> 8.1 / 8.7; G1 4 / 6 / 7 / 8 -> 14.4 / 15.9 / 15.8 / 15.6)
+LANES = {"g1": 6, "g2": 8, "fq12": 16, "fq": 8}
 DTYPE = "u64 (Goldilocks field; BN254 Fq on 8x32-bit limbs)"
 # ncu --set full capture of the trace-commitment launch of k_leaf_hash for the G1 shape (profiles/r02_leaf_hash_ncu_summary.txt):
 # dram read 1.7601 GB + write 9.57 MB = its algorithmic bytes (1676 columns x 2^17 rows x 8 B + digests), no re-reads
@@ -170,7 +173,8 @@ def main():
     ap.add_argument("--num-io", type=int, default=0, help="instances per proof (power of two; default: the AIR's headline size)")
     ap.add_argument("--no-intra-proof", action="store_true", help="skip the sharded single-proof latency measurement at N > 1")
     ap.add_argument("--no-other-airs", action="store_true", help="measure only the headline AIR")
-    ap.add_argument("--inflight", type=int, default=6, help="lanes of the batch = independent proofs in flight per GPU (one CUDA stream + native host thread each)")
+    ap.add_argument("--inflight", type=int, default=0, help="lanes of the batch = independent proofs in flight per GPU (one CUDA stream + native host thread each); "
+                    "0 = the AIR's default (LANES: the small proofs of Fq12 / Fq need more of them in flight to fill the machine)")
     ap.add_argument("--sweep", default=None, choices=["modular"], help="BASELINE.json configs[4]: one JSON line per (rows, rate_bits) point")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -199,7 +203,11 @@ def main():
     sbn = entry.load_package()
     from starky_bn254_b200 import sharding
     stream = torch.cuda.current_stream()
-    lanes = max(1, args.inflight)
+    host_threads = max(6, (os.cpu_count() or 16) // max(world, 1))   # one native host thread per lane and rank
+
+    def lanes_for(air):
+        return max(1, args.inflight) if args.inflight else min(LANES[air], host_threads)
+    lanes = lanes_for(args.air)
     batch = sbn.Batch(local, lanes)
     head = AirBench(sbn, torch, batch, local, rank, args.air, args.num_io)
     stark, cfg, syn = head.stark, head.cfg, sbn.synthetic
@@ -260,17 +268,23 @@ def main():
     # ---- the other AIRs the metric names (same batch, fewer steps) ----
     others = {}
     if not args.no_other_airs and args.air == "g1" and not args.num_io:
-        osteps = max(4, args.steps // 2)
+        obatch, olanes = batch, lanes
         for name in ("g2", "fq12", "fq"):
             try:
-                batch.trim()   # the lanes' allocators cache the previous AIR's block sizes
-                ab = AirBench(sbn, torch, batch, local, rank, name, 0)
-                ab.resident(0, lanes)
+                obatch.trim()   # the lanes' allocators cache the previous AIR's block sizes
+                if lanes_for(name) != olanes:
+                    if obatch is not batch:
+                        obatch.close()
+                    olanes = lanes_for(name)
+                    obatch = batch if olanes == lanes else sbn.Batch(local, olanes)
+                ab = AirBench(sbn, torch, obatch, local, rank, name, 0)
+                osteps = max(4, args.steps // 2, olanes)   # at least one proof per lane
+                ab.resident(0, olanes)
                 oms, _, _ = timed(ab.resident, 0, osteps)
-                ab.e2e(0, min(lanes, 2))
+                ab.e2e(0, olanes)   # every lane's pinned staging arena exists before the timed region
                 _, oe2e, ob = timed(ab.e2e, 0, osteps)
                 oms, oe2e = sharding.max_over_ranks([oms, oe2e], device="cuda")
-                others[name] = {"metric": ab.metric, "workload": AIRS[name][5], "steps": osteps, "value": world * osteps / (oms / 1e3), "ms_per_step": oms / osteps,
+                others[name] = {"metric": ab.metric, "workload": AIRS[name][5], "steps": osteps, "lanes": olanes, "value": world * osteps / (oms / 1e3), "ms_per_step": oms / osteps,
                                 "e2e": {"value": world * osteps / (oe2e / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": ab.h2d_bytes(), "d2h_bytes_per_step": len(ob[-1])},
                                 "poseidon_perms_per_proof": ab.perms_per_proof(), "proof_sha256": hashlib.sha256(ob[-1]).hexdigest()[:16]}
                 del ab

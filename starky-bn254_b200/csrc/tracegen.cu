@@ -579,8 +579,8 @@ static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   { KScope ks(ctx, "g1_rows"); k_g1_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx); }
   // results: b on the last row of each block = B[256]
   std::vector<u32> res(n * 16);
-  for (size_t i = 0; i < n; i++)
-    CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 16, aff + ((i * 2 + 1) * 257 + 256) * 16, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  // one strided copy: instance i's result sits (2 * 257 * 16) words after instance i-1's
+  CUDA_CHECK(cudaMemcpy2DAsync(res.data(), 64, aff + (size_t)(257 + 256) * 16, (size_t)2 * 257 * 16 * 4, 64, n, cudaMemcpyDeviceToHost, ctx->stream));
   const int sf = 384, pp = sf + 14, iop = pp + 2, lookups = iop + 1 + 4 * (int)n;
   Inv64 inv;
   for (int c = 0; c < 64; c++) inv.v[c] = c == 63 ? 0 : gl_inv(gl_sub((u64)c, 63));
@@ -680,7 +680,7 @@ static void generate_fq(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   { KScope ks(ctx, "fq_chain"); k_fq_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, chain, err); LAUNCH_CHECK(ctx); }
   { KScope ks(ctx, "fq_rows"); k_fq_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, chain, d_cols, N); LAUNCH_CHECK(ctx); }
   std::vector<u32> res(n * 8);
-  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 8, chain + ((i * 2 + 1) * 257 + 256) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaMemcpy2DAsync(res.data(), 32, chain + (size_t)(257 + 256) * 8, (size_t)2 * 257 * 8 * 4, 32, n, cudaMemcpyDeviceToHost, ctx->stream));
   generate_exp_tail(ctx, air, d_cols, {144, 14, true, 512, 0, 9 * 16 - 1, false});
   check_chain_error(ctx, err, "FqExpStark: internal error");
   if (h_results) memcpy(h_results, res.data(), n * 32);
@@ -759,7 +759,7 @@ static void generate_g2(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   { KScope ks(ctx, "g2_affine"); k_g2_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx); }
   { KScope ks(ctx, "g2_rows"); k_g2_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx); }
   std::vector<u32> res(n * 32);
-  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 32, aff + ((i * 2 + 1) * 257 + 256) * 32, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaMemcpy2DAsync(res.data(), 128, aff + (size_t)(257 + 256) * 32, (size_t)2 * 257 * 32 * 4, 128, n, cudaMemcpyDeviceToHost, ctx->stream));
   generate_exp_tail(ctx, air, d_cols, {768, 14, true, 512, 0, 48 * 16 - 6, false});
   check_chain_error(ctx, err, "degenerate G2 input: the chain hit the point at infinity or two points with equal x (the reference panics here)");
   if (h_results) memcpy(h_results, res.data(), n * 128);
@@ -871,7 +871,7 @@ static void generate_fq12(sbn_ctx* ctx, const AirDesc& air, const void* ios, boo
   { KScope ks(ctx, "fq12_chain"); k_fq12_chain<<<(unsigned)n, 288, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, err); LAUNCH_CHECK(ctx); }
   { KScope ks(ctx, "fq12_rows"); k_fq12_rows<<<(unsigned)(N / 32), 384, 0, ctx->stream>>>(d_ios, io_size, nbits, u64v, chain, d_cols, N); LAUNCH_CHECK(ctx); }
   std::vector<u32> res(n * 96);
-  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaMemcpyAsync(res.data() + i * 96, chain + i * per_inst + (size_t)(nbits + 1) * 96 + (size_t)nbits * 96, 384, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaMemcpy2DAsync(res.data(), 384, chain + (size_t)(nbits + 1) * 96 + (size_t)nbits * 96, per_inst * 4, 384, n, cudaMemcpyDeviceToHost, ctx->stream));
   generate_exp_tail(ctx, air, d_cols, {108 * 16, u64v ? 6 : 14, !u64v, 2 * nbits, 24 * 16, 84 * 16 - 12, true});
   check_chain_error(ctx, err, "Fq12ExpStark: internal error");
   if (h_results) memcpy(h_results, res.data(), n * 384);
