@@ -57,6 +57,27 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) { u32 r; asm("prmt.b3
 // shifts are PRMTs, (c3 mod 2^16) 2^16 + h is one PRMT (rotation by 16), and every add of the stitch is part of a carry chain.
 __device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b, u32 c) { u32 r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ u32 dp2a_hi(u32 a, u32 b, u32 c) { u32 r; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+// the four digit sums of one output lane -> its 64-bit representative (comment above)
+__device__ __forceinline__ u64 poseidon_stitch(u32 c0, u32 c1, u32 c2, u32 c3) {
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 rot, a, b, t1, t, e;\n\t"
+      "prmt.b32 rot, %5, %5, 0x1032;\n\t"        // (c3 << 16) | (c3 >> 16) = (c3 mod 2^16) 2^16 + h
+      "dp2a.lo.u32.s32 a, %5, 0xFF00, %2;\n\t"    // c0 + 0 * (c3 mod 2^16) - 1 * (c3 >> 16) = c0 - h
+      "prmt.b32 t1, %3, 0, 0x1044;\n\t"          // c1 << 16
+      "shf.r.clamp.b32 b, %3, 0, 16;\n\t"         // c1 >> 16
+      "add.u32 b, b, %4;\n\t"
+      "add.cc.u32 %0, a, t1;\n\t"
+      "addc.cc.u32 %1, b, rot;\n\t"
+      "addc.u32 t, 0x7FFFFFFF, 0;\n\t"            // bit 31 = carry (never mix add.cc with subc: ptxas keeps the carry as NOT borrow)
+      "prmt.b32 e, t, 0, 0xBBBB;\n\t"             // sign of byte 3 replicated: 0xFFFFFFFF (= 2^32 - 1 as a 64-bit addend) after a wrap
+      "add.cc.u32 %0, %0, e;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(c0), "r"(c1), "r"(c2), "r"(c3));
+  return ((u64)r1 << 32) | r0;
+}
 __device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], const uint4* __restrict__ rc /* this layer's 12 biased digit quads */) {
   u32 A[4][6];   // A[d][j] = 16-bit digit d of lanes 2j (low half) and 2j+1 (high half)
 #pragma unroll
@@ -75,26 +96,84 @@ __device__ __forceinline__ void poseidon_mds_dp2a(u64 s[12], const uint4* __rest
 #pragma unroll
       for (int d = 0; d < 4; d++) { c[d] = dp2a_lo(A[d][2 * q], m, c[d]); c[d] = dp2a_hi(A[d][2 * q + 1], m, c[d]); }
     }
-    u32 r0, r1;
-    asm("{\n\t"
-        ".reg .u32 rot, a, b, t1, t, e;\n\t"
-        "prmt.b32 rot, %5, %5, 0x1032;\n\t"        // (c3 << 16) | (c3 >> 16) = (c3 mod 2^16) 2^16 + h
-        "dp2a.lo.u32.s32 a, %5, 0xFF00, %2;\n\t"    // c0 + 0 * (c3 mod 2^16) - 1 * (c3 >> 16) = c0 - h
-        "prmt.b32 t1, %3, 0, 0x1044;\n\t"          // c1 << 16
-        "shf.r.clamp.b32 b, %3, 0, 16;\n\t"         // c1 >> 16
-        "add.u32 b, b, %4;\n\t"
-        "add.cc.u32 %0, a, t1;\n\t"
-        "addc.cc.u32 %1, b, rot;\n\t"
-        "addc.u32 t, 0x7FFFFFFF, 0;\n\t"            // bit 31 = carry (never mix add.cc with subc: ptxas keeps the carry as NOT borrow)
-        "prmt.b32 e, t, 0, 0xBBBB;\n\t"             // sign of byte 3 replicated: 0xFFFFFFFF (= 2^32 - 1 as a 64-bit addend) after a wrap
-        "add.cc.u32 %0, %0, e;\n\t"
-        "addc.u32 %1, %1, 0;\n\t"
-        "}"
-        : "=&r"(r0), "=&r"(r1)
-        : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
-    s[r] = ((u64)r1 << 32) | r0;
+    s[r] = poseidon_stitch(c[0], c[1], c[2], c[3]);
   }
 }
+
+#endif
+#ifdef __CUDACC__
+// ---- two lanes per permutation (small trees) ----
+// A tree with few leaves cannot fill the machine with one permutation per thread: 2^14 leaves are 0.86 warps per scheduler, and a
+// lone warp runs the permutation's dependent chains at ~0.5 instructions per clock (28 ms for the 1 225 absorptions of an Fq12
+// trace row whatever the launch shape, tools/microbench).  Here lanes 2t and 2t+1 of a warp share a permutation: role r = lane & 1
+// holds state elements 6r .. 6r+5 (local index i <-> global 6r + i), so a tree has twice the warps and each does half the work.
+//  * S-boxes: six per lane in a full round; in a partial round both lanes run the S-box of local element 0 and role 1 keeps its
+//    old value (same instruction stream, no divergence);
+//  * MDS: the matrix is circulant, so in LOCAL indexing (own six elements first, then the partner's six) the rows of a lane's six
+//    outputs are the first six rows of the same matrix for either role -- the unsplit code with the partner's digit words fetched
+//    by 12 shuffles; only the diagonal term (8 s_0 into output 0) belongs to role 0 alone;
+//  * round constants come from a shared-memory copy of the digit table (the index depends on the lane).
+// State stays in the lazy representation across the permutations of a sponge; the caller canonicalises what leaves it.
+struct PoseidonPairTables { uint4 dig[372]; u64 first[12]; };   // shared memory, filled by poseidon_pair_load_tables
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void poseidon_pair_load_tables(PoseidonPairTables* t) {
+  for (int i = threadIdx.x; i < 372; i += blockDim.x) t->dig[i] = reinterpret_cast<const uint4*>(d_poseidon_rc_dig16)[i];
+  for (int i = threadIdx.x; i < 12; i += blockDim.x) t->first[i] = d_poseidon_rc[i];
+  __syncthreads();
+}
+__device__ __forceinline__ void poseidon_mds_dp2a_pair(u64 s[6], const uint4* __restrict__ rc /* digit quads of this lane's six outputs */, u32 diag8) {
+  u32 A[4][6];   // [d][0..2]: own lane pairs, [d][3..5]: the partner's
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const u32 al = (u32)s[2 * j], ah = (u32)(s[2 * j] >> 32), bl = (u32)s[2 * j + 1], bh = (u32)(s[2 * j + 1] >> 32);
+    A[0][j] = prmt(al, bl, 0x5410); A[1][j] = prmt(al, bl, 0x7632);
+    A[2][j] = prmt(ah, bh, 0x5410); A[3][j] = prmt(ah, bh, 0x7632);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int d = 0; d < 4; d++) A[d][3 + j] = __shfl_xor_sync(0xffffffffu, A[d][j], 1);
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const uint4 k = rc[r];
+    u32 c[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const u32 m = SBN_MDS_WORD((4 * q + 12 - r) % 12) + ((r == 0 && q == 0) ? diag8 : 0u);
+#pragma unroll
+      for (int d = 0; d < 4; d++) { c[d] = dp2a_lo(A[d][2 * q], m, c[d]); c[d] = dp2a_hi(A[d][2 * q + 1], m, c[d]); }
+    }
+    s[r] = poseidon_stitch(c[0], c[1], c[2], c[3]);
+  }
+}
+// s = this lane's six state elements (arbitrary representatives in and out); every lane of the warp must call it.
+__device__ __forceinline__ void poseidon_permute_pair(u64 s[6], int role, const PoseidonPairTables* t) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) s[i] = gl_add_nc(s[i], t->first[6 * role + i]);
+  const uint4* rc = t->dig + 12 + 6 * role;
+  const u32 diag8 = role ? 0u : 8u;
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++, rc += 12) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) s[i] = poseidon_sbox_nc(s[i]);
+      poseidon_mds_dp2a_pair(s, rc, diag8);
+    }
+    if (half == 0) {
+#pragma unroll 1
+      for (int k = 0; k < 22; k++, rc += 12) {
+        const u64 y = poseidon_sbox_nc(s[0]);
+        s[0] = role ? s[0] : y;
+        poseidon_mds_dp2a_pair(s, rc, diag8);
+      }
+    }
+  }
+}
+#else
+__device__ void poseidon_pair_load_tables(PoseidonPairTables* t);
+__device__ void poseidon_permute_pair(u64 s[6], int role, const PoseidonPairTables* t);
+#endif
 #endif
 
 HD u64 poseidon_sbox(u64 x) {

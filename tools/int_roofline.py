@@ -44,10 +44,10 @@ def classify(op):
 
 def kernel_sass(lib=LIB, kernel=KERNEL):
     names = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout   # cheap symbol scan for the mangled name
-    m = re.search(r"(_Z\d+%s\w*)" % kernel, names)
-    if not m:
+    cands = sorted(set(x for x in re.findall(r"(_Z\d+%s\w*)" % kernel, names) if "_param_" not in x), key=len)   # shortest = the kernel itself, not k_leaf_hash_pair<..>
+    if not cands:
         raise RuntimeError("kernel %s not found in %s" % (kernel, lib))
-    out = subprocess.run(["cuobjdump", "-sass", "-fun", m.group(1), lib], capture_output=True, text=True).stdout
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", cands[0], lib], capture_output=True, text=True).stdout
     ins = []
     for line in out.split("\n"):
         mm = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)(.*?);", line)

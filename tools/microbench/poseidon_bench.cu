@@ -29,6 +29,40 @@ template <int BS, int MINB> __global__ void __launch_bounds__(BS, MINB) k_leaf(c
   ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + idx * 4);
   d[0] = make_ulonglong2(st[0], st[1]); d[1] = make_ulonglong2(st[2], st[3]);
 }
+#ifndef POSEIDON_R01
+// two lanes per leaf (poseidon_permute_pair): role 0 absorbs columns c .. c+5, role 1 columns c+6, c+7
+template <int BS> __global__ void __launch_bounds__(BS) k_leaf_pair(const u64* __restrict__ lde, size_t L, int ncols, u64* __restrict__ digests) {
+  __shared__ PoseidonPairTables tab;
+  poseidon_pair_load_tables(&tab);
+  const size_t gt = blockIdx.x * (size_t)blockDim.x + threadIdx.x, idx = gt >> 1;
+  const int role = (int)(gt & 1);
+  if (idx >= L) return;   // L is a multiple of 16: whole warps leave together
+  u64 st[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) st[i] = 0;
+  const u64* p = lde + idx;
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 8) {
+    const int c0 = c + 6 * role, n = role ? 2 : 6;
+#pragma unroll
+    for (int i = 0; i < 6; i++) if (i < n && c0 + i < ncols) st[i] = p[(size_t)(c0 + i) * L];
+    poseidon_permute_pair(st, role, &tab);
+  }
+  if (role == 0) {
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + idx * 4);
+    d[0] = make_ulonglong2(gl_canon(st[0]), gl_canon(st[1])); d[1] = make_ulonglong2(gl_canon(st[2]), gl_canon(st[3]));
+  }
+}
+template <int BS> float run_pair(const u64* lde, size_t L, int ncols, u64* dig, int iters) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  k_leaf_pair<BS><<<(unsigned)((2 * L + BS - 1) / BS), BS>>>(lde, L, ncols, dig);
+  cudaEventRecord(a);
+  for (int i = 0; i < iters; i++) k_leaf_pair<BS><<<(unsigned)((2 * L + BS - 1) / BS), BS>>>(lde, L, ncols, dig);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  return ms / iters;
+}
+#endif
 __global__ void k_fill(u64* p, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -55,7 +89,12 @@ int main(int argc, char** argv) {
   float ms;
 #define RUN(BS, MINB) ms = run<BS, MINB>(lde, L, ncols, dig, 3); cudaMemcpy(h.data(), dig + 4 * 777, 32, cudaMemcpyDeviceToHost); \
   printf("%s bs=%d minb=%d  %.3f ms  %.1f Mperm/s  dig=%016llx\n", VARIANT, BS, MINB, ms, perms / ms / 1e3, h[0]);
-  RUN(128, 1) RUN(128, 6) RUN(128, 8) RUN(64, 14) RUN(256, 3)
+  RUN(128, 1) RUN(128, 6) RUN(128, 8) RUN(64, 14) RUN(256, 3) RUN(32, 1) RUN(64, 1) RUN(32, 16) RUN(64, 4)
+#ifndef POSEIDON_R01
+#define RUNP(BS) ms = run_pair<BS>(lde, L, ncols, dig, 3); cudaMemcpy(h.data(), dig + 4 * 777, 32, cudaMemcpyDeviceToHost); \
+  printf("pair    bs=%d          %.3f ms  %.1f Mperm/s  dig=%016llx\n", BS, ms, perms / ms / 1e3, h[0]);
+  RUNP(64) RUNP(128) RUNP(256)
+#endif
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
   return 0;

@@ -15,7 +15,7 @@ pat = re.compile(r"^(Kernel Name|gpu__time_duration\.sum|dram__bytes_read\.sum|d
                  r"sm__pipe_fma_cycles_active\.avg\.pct_of_peak_sustained_active|sm__pipe_alu_cycles_active\.avg\.pct_of_peak_sustained_active|"
                  r"smsp__warps_active\.avg\.per_cycle_active|smsp__warps_eligible\.avg\.per_cycle_active|sm__warps_active\.avg\.pct_of_peak_sustained_active|"
                  r"smsp__average_warps_issue_stalled_.*_per_issue_active\.ratio|l1tex__t_sector_hit_rate\.pct|lts__t_sector_hit_rate\.pct|"
-                 r"smsp__inst_executed_op_local_(ld|st)\.sum|sm__throughput\.avg\.pct_of_peak_sustained_elapsed)$")
+                 r"smsp__inst_executed_op_local_(ld|st)\.sum|smsp__thread_inst_executed_per_inst_executed\.ratio|l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum|sm__throughput\.avg\.pct_of_peak_sustained_elapsed)$")
 for r in rows[2:]:
     print("----")
     for i, h in enumerate(hdr):
