@@ -95,6 +95,26 @@ __global__ void __launch_bounds__(128) k_merkle_level(const u64* __restrict__ ch
   d[1] = make_ulonglong2(st[2], st[3]);
 }
 
+// two_to_one with two lanes per parent for the small upper levels (one permutation of latency per level either way: 23 us
+// with one thread per parent, about half with two lanes): role 0 holds the left child and half of the right, role 1 the rest.
+__global__ void __launch_bounds__(128) k_merkle_level_pair(const u64* __restrict__ child, u64* __restrict__ parent, size_t nparents) {
+  __shared__ PoseidonPairTables tab;
+  poseidon_pair_load_tables(&tab);
+  const size_t gt = blockIdx.x * (size_t)blockDim.x + threadIdx.x, i = gt >> 1;
+  const int role = (int)(gt & 1);
+  if (i >= nparents) return;   // nparents is a multiple of 16: whole warps leave together
+  const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);
+  u64 st[6] = {0, 0, 0, 0, 0, 0};
+  if (role == 0) { const ulonglong2 a0 = c[0], a1 = c[1], b0 = c[2]; st[0] = a0.x; st[1] = a0.y; st[2] = a1.x; st[3] = a1.y; st[4] = b0.x; st[5] = b0.y; }
+  else { const ulonglong2 b1 = c[3]; st[0] = b1.x; st[1] = b1.y; }
+  poseidon_permute_pair(st, role, &tab);
+  if (role == 0) {
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(parent + i * 4);
+    d[0] = make_ulonglong2(gl_canon(st[0]), gl_canon(st[1]));
+    d[1] = make_ulonglong2(gl_canon(st[2]), gl_canon(st[3]));
+  }
+}
+
 void merkle_alloc(sbn_ctx* ctx, DevMerkleTree* t, size_t nleaves, int cap_height) {
   SBN_REQUIRE(nleaves >= (size_t(1) << cap_height), "merkle: fewer leaves than cap entries");
   t->nleaves = nleaves; t->cap_height = cap_height;
@@ -109,7 +129,10 @@ void merkle_build_from_leaf_digests(sbn_ctx* ctx, DevMerkleTree* t) {
   KScope ks(ctx, "merkle_tree_levels");
   for (int l = 0; l + 1 < t->num_levels(); l++) {
     size_t np = n >> 1;
-    k_merkle_level<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(t->digests + t->level_off[l], t->digests + t->level_off[l + 1], np);
+    if (np >= 16 && np <= (size_t(1) << 13) && !getenv("SBN_LEAF_HASH_ONE_THREAD"))
+      k_merkle_level_pair<<<(unsigned)((2 * np + 127) / 128), 128, 0, ctx->stream>>>(t->digests + t->level_off[l], t->digests + t->level_off[l + 1], np);
+    else
+      k_merkle_level<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(t->digests + t->level_off[l], t->digests + t->level_off[l + 1], np);
     LAUNCH_CHECK(ctx);
     n = np;
   }

@@ -1,0 +1,11 @@
+#!/bin/bash
+# GPU session AC (8 GPUs): the driver's scaling command on the final build (replicas + intra-proof latency), then config 5 at 2^22 rows sharded.
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2ac_bench_8gpu.json 2> gpurun_out/r2ac_bench_8gpu.err; echo "bench8 rc=$?" >> gpurun_out/r2ac_bench_8gpu.err
+tail -2 gpurun_out/r2ac_bench_8gpu.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r2ac_bench_8gpu.json").read().strip().split("\n")[-1])
+ip = d.get("intra_proof") or {}
+print(d["n_gpus"], d["steps"], round(d["value"], 2), round(d["e2e"]["value"], 2), {k: (v.get("lanes"), round(v.get("value", 0), 2)) if "error" not in v else v for k, v in d.get("airs", {}).items()}, "intra", ip.get("ms_per_proof"), ip.get("phase_ms_rank0"))
+PY
