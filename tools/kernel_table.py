@@ -39,14 +39,15 @@ for lid, m in per.items():
     a["issue_t"] += t * m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", (0, ""))[0]
     a["fmah_t"] += t * m.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", (0, ""))[0]
     a["alu_t"] += t * m.get("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", (0, ""))[0]
+    a["lanes_i"] += m.get("smsp__thread_inst_executed_per_inst_executed.ratio", (0, ""))[0] * m.get("smsp__inst_executed.sum", (0, ""))[0]   # optional metric
 total = sum(a["t"] for a in agg.values())
 print("HBM peak %.1f GB/s (MEASURED_PEAKS.json); one G1 proof incl. trace generation; per kernel, all launches" % peak)
-print("%-34s %6s %9s %6s %9s %8s %7s %7s %7s %7s" % ("kernel", "n", "ms", "share", "DRAM MB", "GB/s", "HBM%", "issue%", "mulpipe%", "alu%"))
+print("%-34s %6s %9s %6s %9s %8s %7s %7s %7s %7s %6s" % ("kernel", "n", "ms", "share", "DRAM MB", "GB/s", "HBM%", "issue%", "mulpipe%", "alu%", "lanes"))
 for k in sorted(agg, key=lambda k: -agg[k]["t"]):
     a = agg[k]
     if a["t"] < total * 0.002:
         continue
     gbs = a["bytes"] / a["t"] / 1e9
-    print("%-34s %6d %9.3f %5.1f%% %9.1f %8.1f %6.1f%% %6.1f%% %7.1f%% %6.1f%%" % (k[:34], a["n"], a["t"] * 1e3, 100 * a["t"] / total, a["bytes"] / 1e6, gbs,
-          100 * gbs / peak, a["issue_t"] / a["t"], a["fmah_t"] / a["t"], a["alu_t"] / a["t"]))
+    print("%-34s %6d %9.3f %5.1f%% %9.1f %8.1f %6.1f%% %6.1f%% %7.1f%% %6.1f%% %6.1f" % (k[:34], a["n"], a["t"] * 1e3, 100 * a["t"] / total, a["bytes"] / 1e6, gbs,
+          100 * gbs / peak, a["issue_t"] / a["t"], a["fmah_t"] / a["t"], a["alu_t"] / a["t"], a["lanes_i"] / a["inst"] if a["inst"] else 0.0))   # lanes = active threads per warp instruction
 print("%-34s %6d %9.3f" % ("total", sum(a["n"] for a in agg.values()), total * 1e3))
