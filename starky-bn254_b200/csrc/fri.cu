@@ -20,24 +20,51 @@ static void launch_ext_powers(sbn_ctx* ctx, u64* out_a, u64* out_b, gl2 base, si
 }
 
 // ---- openings ----
-// One block per column; reads the column once (coalesced), multiplies by the shared power tables.
-__global__ void __launch_bounds__(256) k_eval_two_points(const u64* __restrict__ coeffs, size_t N, const u64* __restrict__ pw /* [4][N]: z.a z.b zn.a zn.b */,
-                                                         u64* __restrict__ out) {
-  const u64* col = coeffs + (size_t)blockIdx.x * N;
-  gl_acc a0 = gl_acc_zero(), a1 = gl_acc_zero(), a2 = gl_acc_zero(), a3 = gl_acc_zero();   // unreduced sums of products
-  for (size_t j = threadIdx.x; j < N; j += blockDim.x) {
-    u64 c = col[j];
-    gl_acc_mac(a0, c, pw[j]); gl_acc_mac(a1, c, pw[N + j]);
-    gl_acc_mac(a2, c, pw[2 * N + j]); gl_acc_mac(a3, c, pw[3 * N + j]);
+// One block per COLS columns; a column is read once (coalesced) and multiplied by the power tables, which every block streams from
+// L2 (the blocks of a wave walk the tables at the same pace).  Shape chosen by measurement on the G1 trace (gpurun_out/r2ag_*, ms
+// per proof): all five loads of an iteration issued before the four multiply-accumulates, one column per block, one iteration
+// in flight: 1.00; the same loop with the loads written inside the multiply-accumulate calls: 1.41; four iterations in flight:
+// 1.61; two / three columns per block sharing each table load: 1.71 / 2.15.
+template <int COLS, int U> __global__ void __launch_bounds__(256) k_eval_two_points(const u64* __restrict__ coeffs, size_t N, int ncols,
+                                                                                    const u64* __restrict__ pw /* [4][N]: z.a z.b zn.a zn.b */, u64* __restrict__ out) {
+  const int c0 = blockIdx.x * COLS;
+  const u64* col[COLS];
+#pragma unroll
+  for (int c = 0; c < COLS; c++) col[c] = coeffs + (size_t)min(c0 + c, ncols - 1) * N;   // a ragged last block recomputes the last column
+  gl_acc acc[COLS][4];
+#pragma unroll
+  for (int c = 0; c < COLS; c++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc[c][k] = gl_acc_zero();   // unreduced sums of products
+#pragma unroll 1
+  for (size_t j0 = threadIdx.x; j0 < N; j0 += (size_t)blockDim.x * U) {   // U > 1 needs N to be a multiple of 256 U
+    u64 v[U][COLS], p[U][4];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t j = j0 + (size_t)u * blockDim.x;
+#pragma unroll
+      for (int c = 0; c < COLS; c++) v[u][c] = col[c][j];
+#pragma unroll
+      for (int k = 0; k < 4; k++) p[u][k] = pw[(size_t)k * N + j];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int c = 0; c < COLS; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) gl_acc_mac(acc[c][k], v[u][c], p[u][k]);
   }
-  __shared__ u64 red[4][256];
-  red[0][threadIdx.x] = gl_acc_reduce(a0); red[1][threadIdx.x] = gl_acc_reduce(a1); red[2][threadIdx.x] = gl_acc_reduce(a2); red[3][threadIdx.x] = gl_acc_reduce(a3);
+  __shared__ u64 red[COLS * 4][256];
+#pragma unroll
+  for (int c = 0; c < COLS; c++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) red[c * 4 + k][threadIdx.x] = gl_acc_reduce(acc[c][k]);
   __syncthreads();
   for (int d = 128; d > 0; d >>= 1) {
-    if ((int)threadIdx.x < d) for (int k = 0; k < 4; k++) red[k][threadIdx.x] = gl_add(red[k][threadIdx.x], red[k][threadIdx.x + d]);
+    if ((int)threadIdx.x < d) for (int k = 0; k < COLS * 4; k++) red[k][threadIdx.x] = gl_add(red[k][threadIdx.x], red[k][threadIdx.x + d]);
     __syncthreads();
   }
-  if (threadIdx.x < 4) out[(size_t)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
+  if (threadIdx.x < COLS * 4 && c0 + (int)(threadIdx.x >> 2) < ncols) out[(size_t)c0 * 4 + threadIdx.x] = red[threadIdx.x][0];
 }
 
 DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1) {
@@ -51,7 +78,8 @@ DevBuf<u64> two_point_power_table(sbn_ctx* ctx, int logn, gl2 z0, gl2 z1) {
 void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, const u64* pw, u64* d_out) {
   if (ncols <= 0) return;
   KScope ks(ctx, "openings_eval");
-  k_eval_two_points<<<ncols, 256, 0, ctx->stream>>>(coeffs, size_t(1) << logn, pw, d_out);
+  const size_t N = size_t(1) << logn;
+  k_eval_two_points<1, 1><<<ncols, 256, 0, ctx->stream>>>(coeffs, N, ncols, pw, d_out);
   LAUNCH_CHECK(ctx);
 }
 void eval_columns_at_two_points(sbn_ctx* ctx, const u64* coeffs, int ncols, int logn, gl2 zeta, gl2 zeta_next, u64* d_out) {

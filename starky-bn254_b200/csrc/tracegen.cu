@@ -221,7 +221,7 @@ __device__ __forceinline__ int lwp_next_smaller(const u16* H, int u, u32 x, bool
   return res;
 }
 __global__ void __launch_bounds__(LWP_THREADS, 1) k_lookup_walk_parallel(const u32* __restrict__ cnt_all, size_t N, u64* __restrict__ cols, const LookupDesc* __restrict__ descs,
-                                                                         u32* __restrict__ stack_all, u32* __restrict__ scratch_all) {
+                                                                         u32* __restrict__ stack_all, u32* __restrict__ scratch_all, u32 huge_cap /* <= LWP_HUGE */) {
   extern __shared__ __align__(16) unsigned char lwp_smem[];
   u16* H = reinterpret_cast<u16*>(lwp_smem);
   u16* tree = H + LWP_R;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(LWP_THREADS, 1) k_lookup_walk_parallel(const u
       if (c <= 32) for (u32 t = 0; t < c; t++) sorted[off + t] = v;
       const u32 hp = v ? (u32)H[lwp_swz(v - 1)] : 0u;
       if (c - 1 > hp) any_deferred = true;
-      if (c > LWP_HUGE_MIN) { const u32 slot = atomicAdd(&misc[1], 1u); if (slot < LWP_HUGE) huge[slot] = v; }
+      if (c > LWP_HUGE_MIN) { const u32 slot = atomicAdd(&misc[1], 1u); if (slot < huge_cap) huge[slot] = v; }
     }
     u32 big = __ballot_sync(FULL, live && c > 32 && c <= LWP_HUGE_MIN);
     while (big) {
@@ -349,17 +349,17 @@ __global__ void __launch_bounds__(LWP_THREADS, 1) k_lookup_walk_parallel(const u
     }
   }
   any_deferred = __syncthreads_or(any_deferred);   // leftover[] and huge[] complete
-  const u32 nhuge = misc[1];                        // > LWP_HUGE: the list overflowed, the values beyond it are written by their warps
+  const u32 nhuge = misc[1];                        // > huge_cap: the list overflowed, the values beyond it are written by their warps
   // ---- pass 4: deferred positions take the leftover stack bottom-first, then the table's last value ----
 #pragma unroll 1
   for (int j = 0; j < (int)(R / 32 / 32); j++) {
-    if (!any_deferred && nhuge <= LWP_HUGE) break;
+    if (!any_deferred && nhuge <= huge_cap) break;
     const u32 v = wbase + j * 32 + lane;
     const u32 c = cnt[v];
     const bool live = v != R - 1;
     const u32 hp = v ? (u32)H[lwp_swz(v - 1)] : 0u;
     bool listed = false;
-    if (live && c > LWP_HUGE_MIN) for (u32 e = 0; e < min(nhuge, (u32)LWP_HUGE); e++) listed |= huge[e] == v;
+    if (live && c > LWP_HUGE_MIN) for (u32 e = 0; e < min(nhuge, huge_cap); e++) listed |= huge[e] == v;
     const u32 nd = (live && !listed && c >= 2 && c - 1 > hp) ? c - 1 - hp : 0u;
     const bool fill = live && !listed && c > LWP_HUGE_MIN;   // a long run that did not fit the list
     if (!__ballot_sync(FULL, nd > 0 || fill)) continue;
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(LWP_THREADS, 1) k_lookup_walk_parallel(const u
       }
     }
   }
-  for (u32 e = 0; e < min(nhuge, (u32)LWP_HUGE); e++) {   // the longest runs: sorted copies and deferred positions by the whole block
+  for (u32 e = 0; e < min(nhuge, huge_cap); e++) {   // the longest runs: sorted copies and deferred positions by the whole block
     const u32 v = huge[e], c = cnt[v], off = off0g[v], hp = v ? (u32)H[lwp_swz(v - 1)] : 0u, D = v ? dg[v - 1] : 0u;
     const u32 npop = min(c - 1, hp), nd = c - 1 - npop;
     for (u32 t = tid; t < c; t += LWP_THREADS) sorted[off + t] = v;
@@ -410,6 +410,9 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
   const bool sequential = getenv("SBN_LOOKUP_SEQUENTIAL") != nullptr;
   const char* walk_env = getenv("SBN_LOOKUP_WALK");
   const bool parallel = !sequential && R == (u32)LWP_R && N < (size_t(1) << 31) && !(walk_env && !strcmp(walk_env, "chunked"));
+  // SBN_LOOKUP_HUGE_LIST=n (test switch): capacity of the kernel's list of very long runs, 0 exercises its overflow path
+  const char* huge_env = getenv("SBN_LOOKUP_HUGE_LIST");
+  const u32 huge_cap = huge_env ? (u32)std::min(std::max(atoi(huge_env), 0), (int)LWP_HUGE) : (u32)LWP_HUGE;
   if (parallel) CUDA_CHECK(cudaFuncSetAttribute(k_lookup_walk_parallel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LWP_SMEM));
   if (sequential) group = std::min(group, std::max<size_t>(1, (size_t(512) << 20) / ((N + 2 * (size_t)R) * 4)));
   DevBuf<u32> cnt(ctx, group * R), stack(ctx, group * R);
@@ -424,7 +427,7 @@ static void run_lookups(sbn_ctx* ctx, u64* d_cols, size_t N, u32 R, const std::v
     LAUNCH_CHECK(ctx); }
     KScope ks2(ctx, "lookup_walk");
     if (sequential) k_lookup_walk<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer_seq);
-    else if (parallel) k_lookup_walk_parallel<<<(unsigned)ng, LWP_THREADS, LWP_SMEM, ctx->stream>>>(cnt, N, d_cols, d_desc + g0, stack, reinterpret_cast<u32*>((uint2*)defer));
+    else if (parallel) k_lookup_walk_parallel<<<(unsigned)ng, LWP_THREADS, LWP_SMEM, ctx->stream>>>(cnt, N, d_cols, d_desc + g0, stack, reinterpret_cast<u32*>((uint2*)defer), huge_cap);
     else k_lookup_walk_chunked<<<(unsigned)ng, 32, 0, ctx->stream>>>(cnt, R, N, d_cols, d_desc + g0, stack, defer);
     LAUNCH_CHECK(ctx);
   }

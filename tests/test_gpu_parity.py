@@ -146,6 +146,10 @@ def test_parallel_lookup_walk_matches_walk_kernels(ctx, sbn, monkeypatch, case):
         ios = (ios[:size] + ios[size:2 * size]) * (n // 2)
     g1 = sbn.G1ExpStark(n, ctx)
     a = g1.generate_trace(ios).download()
+    monkeypatch.setenv("SBN_LOOKUP_HUGE_LIST", "0")   # the runs of > 2 048 copies written by their warps instead of the whole block
+    b = g1.generate_trace(ios).download()
+    monkeypatch.delenv("SBN_LOOKUP_HUGE_LIST")
+    assert (a == b).all()
     monkeypatch.setenv("SBN_LOOKUP_WALK", "chunked")
     b = g1.generate_trace(ios).download()
     assert (a == b).all()
