@@ -234,9 +234,9 @@ def main():
     head.resident(0, max(args.warmup, lanes))
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = batch.launch_count
+    launches0, bytes0 = batch.launch_count, batch.device_bytes
     ms_total, _, proofs = timed(head.resident, args.warmup, args.steps)
-    launches = batch.launch_count - launches0
+    launches, pool_growth = batch.launch_count - launches0, batch.device_bytes - bytes0   # growth > 0: a lane called cudaMalloc inside the timed region
     # ---- end to end: pinned host inputs -> proof bytes on the host ----
     head.e2e(0, lanes)
     _, e2e_ms, proof_bytes = timed(head.e2e, args.warmup, args.steps)
@@ -347,7 +347,7 @@ def main():
             "metric": head.metric, "value": world * args.steps / (ms_total / 1e3), "unit": "proofs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config_of(args.air, head.num_io),
-            "inflight_per_gpu": lanes, "api": "sbn_prove_batch: one call per timed region, %d lanes (CUDA stream + native host thread each), one Python thread" % lanes,
+            "inflight_per_gpu": lanes, "allocator_growth_bytes_in_timed_region": pool_growth, "api": "sbn_prove_batch: one call per timed region, %d lanes (CUDA stream + native host thread each), one Python thread" % lanes,
             "instances_per_s": world * args.steps * head.num_io / (ms_total / 1e3),
             "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": head.h2d_bytes(), "d2h_bytes_per_step": len(last_proof_bytes)},
             "airs": others,

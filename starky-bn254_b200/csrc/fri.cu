@@ -95,13 +95,13 @@ __global__ void __launch_bounds__(256) k_reduce_columns(const u64* __restrict__ 
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= N) return;
   int c0 = blockIdx.y * cols_per_group, c1 = min(ncols, c0 + cols_per_group);
-  u64 sa = 0, sb = 0;
+  gl_acc sa = gl_acc_zero(), sb = gl_acc_zero();   // unreduced sums of products, one reduction per output
   for (int c = c0; c < c1; c++) {
-    u64 v = coeffs[(size_t)c * N + i];
-    sa = gl_add(sa, gl_mul(v, apow_a[apow_off + c])); sb = gl_add(sb, gl_mul(v, apow_b[apow_off + c]));
+    const u64 v = coeffs[(size_t)c * N + i];
+    gl_acc_mac(sa, v, apow_a[apow_off + c]); gl_acc_mac(sb, v, apow_b[apow_off + c]);
   }
   u64* p = partial + (size_t)blockIdx.y * 2 * N;
-  p[i] = sa; p[N + i] = sb;
+  p[i] = gl_acc_reduce(sa); p[N + i] = gl_acc_reduce(sb);
 }
 __global__ void k_sum_partials(const u64* partial, int ngroups, size_t N, u64* out /* [2][N] */, int accumulate) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
