@@ -501,6 +501,60 @@ __global__ void __launch_bounds__(64) k_g1_chain(const G1Io* __restrict__ ios, s
     if (live) out[k + 1] = P;
   }
 }
+// The same chains on more of the machine (round 2).  A[k] = 2^k x is inherently sequential (one thread per instance, 256
+// doublings); B[k] = offset + sum_{j<k, bit_j} A[j] is a PREFIX SUM under point addition, which is associative: one block per
+// instance, one thread per bit, a Kogge-Stone scan of the terms bit_j ? A[j] : identity through shared memory (8 rounds of one
+// addition each instead of 256 dependent ones), then one addition of the offset.  The points differ from the sequential chain's
+// only in their Jacobian representation; the affine coordinates the trace is built from are the same field elements.  The
+// identity is Z = 0; a sum of two finite points that comes out with Z = 0 (equal or opposite points) raises the error flag the
+// sequential chain raises through k_g1_affine.
+__global__ void __launch_bounds__(32) k_g1_dbl_chain(const G1Io* __restrict__ ios, size_t num_io, G1Jac* __restrict__ jac /* [io][2][257] */, int* __restrict__ err) {
+  const size_t i = blockIdx.x * (size_t)32 + threadIdx.x;
+  if (i >= num_io) return;
+  const G1Io& io = ios[i];
+  u32 w[8];
+  G1Jac P;
+  u64x4_to_words(io.x_x, w); if (fq_geq_p(w)) *err = 2;
+  P.x = fq_from_words(w);
+  u64x4_to_words(io.x_y, w); if (fq_geq_p(w)) *err = 2;
+  P.y = fq_from_words(w); P.z = fq_one();
+  G1Jac* out = jac + i * 2 * 257;
+  out[0] = P;
+  for (int k = 0; k < 256; k++) { P = g1_jac_dbl(P); out[k + 1] = P; }
+}
+HD G1Jac g1_jac_add_id(const G1Jac& p, const G1Jac& q, int* err) {   // identity-aware
+  if (fq_is_zero(p.z)) return q;
+  if (fq_is_zero(q.z)) return p;
+  G1Jac r = g1_jac_add(p, q);
+  if (fq_is_zero(r.z)) *err = 1;
+  return r;
+}
+__global__ void __launch_bounds__(256) k_g1_sum_scan(const G1Io* __restrict__ ios, G1Jac* __restrict__ jac /* [io][2][257] */, int* __restrict__ err) {
+  __shared__ G1Jac buf[256];
+  const size_t i = blockIdx.x;
+  const int j = threadIdx.x;
+  const G1Io& io = ios[i];
+  G1Jac* A = jac + i * 2 * 257;
+  G1Jac* B = A + 257;
+  G1Jac v;
+  if ((io.exp[j >> 5] >> (j & 31)) & 1) v = A[j];
+  else { v.x = fq_one(); v.y = fq_one(); v.z = fq_zero(); }
+#pragma unroll 1
+  for (int d = 1; d < 256; d <<= 1) {
+    buf[j] = v;
+    __syncthreads();
+    if (j >= d) v = g1_jac_add_id(buf[j - d], v, err);
+    __syncthreads();
+  }
+  u32 w[8];
+  G1Jac off;
+  u64x4_to_words(io.off_x, w); if (fq_geq_p(w)) *err = 2;
+  off.x = fq_from_words(w);
+  u64x4_to_words(io.off_y, w); if (fq_geq_p(w)) *err = 2;
+  off.y = fq_from_words(w); off.z = fq_one();
+  if (j == 0) B[0] = off;
+  B[j + 1] = g1_jac_add_id(off, v, err);
+}
 __global__ void __launch_bounds__(128) k_g1_affine(const G1Jac* __restrict__ jac, size_t npoints, u32* __restrict__ aff /* [point][16] */, int* __restrict__ err) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= npoints) return;
@@ -586,7 +640,14 @@ static void generate_g1(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   const size_t npoints = n * 2 * 257;
   DevBuf<G1Jac> jac(ctx, npoints);
   DevBuf<u32> aff(ctx, npoints * 16);
-  { KScope ks(ctx, "g1_chain"); k_g1_chain<<<(unsigned)((n + 31) / 32), 64, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx); }
+  // SBN_CHAIN=sequential: the two-warp kernel with 256 dependent additions (kept as the cross-check of the scan)
+  const bool seq_chain = getenv("SBN_CHAIN") && !strcmp(getenv("SBN_CHAIN"), "sequential");
+  if (seq_chain) { KScope ks(ctx, "g1_chain"); k_g1_chain<<<(unsigned)((n + 31) / 32), 64, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx); }
+  else {
+    KScope ks(ctx, "g1_chain");
+    k_g1_dbl_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx);
+    k_g1_sum_scan<<<(unsigned)n, 256, 0, ctx->stream>>>(d_ios, jac, err); LAUNCH_CHECK(ctx);
+  }
   { KScope ks(ctx, "g1_affine"); k_g1_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx); }
   { KScope ks(ctx, "g1_rows"); k_g1_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx); }
   // results: b on the last row of each block = B[256]
@@ -723,6 +784,56 @@ __global__ void __launch_bounds__(64) k_g2_chain(const sbn_g2_exp_io* __restrict
     if (live) out[k + 1] = P;
   }
 }
+// G2: doubling chain + prefix-sum scan, as k_g1_dbl_chain / k_g1_sum_scan.
+HD void g2_load_point(const u64* src, G2Jac& P, bool& bad) {
+  u32 w[16];
+  for (int t = 0; t < 4; t++) {
+    u64x4_to_words(src + 4 * t, w); if (fq_geq_p(w)) bad = true;
+    Fq v = fq_from_words(w); (t == 0 ? P.x.c0 : t == 1 ? P.x.c1 : t == 2 ? P.y.c0 : P.y.c1) = v;
+  }
+  P.z = fq2_one();
+}
+__global__ void __launch_bounds__(32) k_g2_dbl_chain(const sbn_g2_exp_io* __restrict__ ios, size_t num_io, G2Jac* __restrict__ jac, int* __restrict__ err) {
+  const size_t i = blockIdx.x * (size_t)32 + threadIdx.x;
+  if (i >= num_io) return;
+  G2Jac P; bool bad = false;
+  g2_load_point((const u64*)ios[i].x, P, bad);
+  if (bad) *err = 2;
+  G2Jac* out = jac + i * 2 * 257;
+  out[0] = P;
+  for (int k = 0; k < 256; k++) { P = g2_jac_dbl(P); out[k + 1] = P; }
+}
+HD G2Jac g2_jac_add_id(const G2Jac& p, const G2Jac& q, int* err) {
+  if (fq2_is_zero(p.z)) return q;
+  if (fq2_is_zero(q.z)) return p;
+  G2Jac r = g2_jac_add(p, q);
+  if (fq2_is_zero(r.z)) *err = 1;
+  return r;
+}
+__global__ void __launch_bounds__(256) k_g2_sum_scan(const sbn_g2_exp_io* __restrict__ ios, G2Jac* __restrict__ jac, int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char g2_scan_smem[];
+  G2Jac* buf = reinterpret_cast<G2Jac*>(g2_scan_smem);
+  const size_t i = blockIdx.x;
+  const int j = threadIdx.x;
+  const sbn_g2_exp_io& io = ios[i];
+  G2Jac* A = jac + i * 2 * 257;
+  G2Jac* B = A + 257;
+  G2Jac v;
+  if ((io.exp_val[j >> 5] >> (j & 31)) & 1) v = A[j];
+  else { v.x = fq2_one(); v.y = fq2_one(); v.z.c0 = fq_zero(); v.z.c1 = fq_zero(); }
+#pragma unroll 1
+  for (int d = 1; d < 256; d <<= 1) {
+    buf[j] = v;
+    __syncthreads();
+    if (j >= d) v = g2_jac_add_id(buf[j - d], v, err);
+    __syncthreads();
+  }
+  G2Jac off; bool bad = false;
+  g2_load_point((const u64*)io.offset, off, bad);
+  if (bad) *err = 2;
+  if (j == 0) B[0] = off;
+  B[j + 1] = g2_jac_add_id(off, v, err);
+}
 __global__ void __launch_bounds__(128) k_g2_affine(const G2Jac* __restrict__ jac, size_t npoints, u32* __restrict__ aff /* [point][32] */, int* __restrict__ err) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= npoints) return;
@@ -767,7 +878,15 @@ static void generate_g2(sbn_ctx* ctx, const AirDesc& air, const void* ios, bool 
   const size_t npoints = n * 2 * 257;
   DevBuf<G2Jac> jac(ctx, npoints);
   DevBuf<u32> aff(ctx, npoints * 32);
-  { KScope ks(ctx, "g2_chain"); k_g2_chain<<<(unsigned)((n + 31) / 32), 64, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx); }
+  const bool seq_chain = getenv("SBN_CHAIN") && !strcmp(getenv("SBN_CHAIN"), "sequential");
+  if (seq_chain) { KScope ks(ctx, "g2_chain"); k_g2_chain<<<(unsigned)((n + 31) / 32), 64, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx); }
+  else {
+    KScope ks(ctx, "g2_chain");
+    const int smem = (int)(256 * sizeof(G2Jac));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2_sum_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_g2_dbl_chain<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(d_ios, n, jac, err); LAUNCH_CHECK(ctx);
+    k_g2_sum_scan<<<(unsigned)n, 256, smem, ctx->stream>>>(d_ios, jac, err); LAUNCH_CHECK(ctx);
+  }
   { KScope ks(ctx, "g2_affine"); k_g2_affine<<<(unsigned)((npoints + 127) / 128), 128, 0, ctx->stream>>>(jac, npoints, aff, err); LAUNCH_CHECK(ctx); }
   { KScope ks(ctx, "g2_rows"); k_g2_rows<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(d_ios, aff, d_cols, N, err); LAUNCH_CHECK(ctx); }
   std::vector<u32> res(n * 32);

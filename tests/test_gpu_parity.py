@@ -131,6 +131,27 @@ def test_lookup_kernels_agree(ctx, sbn, monkeypatch):
     assert (a == b).all()
 
 
+@pytest.mark.parametrize("air,gen", [("G1ExpStark", "g1_exp_ios"), ("G2ExpStark", "g2_exp_ios")])
+def test_prefix_sum_chain_matches_sequential_chain(ctx, sbn, monkeypatch, air, gen):
+    """B[k] = offset + sum_{j<k, bit_j} A[j] as a Kogge-Stone scan under point addition (one block per instance) against the
+    two-warp kernel with 256 dependent additions (SBN_CHAIN=sequential): same trace, also for exponents 0, 1, 2^255 and all ones
+    (terms that are the identity, a prefix that stays the identity)."""
+    n = 128
+    ios = bytearray(getattr(sbn.synthetic, gen)(n, seed=91))
+    stark = getattr(sbn, air)(n, ctx)
+    size = stark.io_size
+    exp_off = {"G1ExpStark": 128, "G2ExpStark": 256}[air]
+    for i, e in enumerate([0, 1, 1 << 255, (1 << 256) - 1, 1 << 31, (1 << 32) | 1]):
+        ios[i * size + exp_off:i * size + exp_off + 32] = e.to_bytes(32, "little")
+    ios = bytes(ios)
+    a = stark.generate_trace(ios)
+    ra, a = a.results().copy(), a.download()
+    monkeypatch.setenv("SBN_CHAIN", "sequential")
+    b = stark.generate_trace(ios)
+    rb, b = b.results().copy(), b.download()
+    assert (a == b).all() and (ra == rb).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["uniform", "one_instance_repeated", "two_instances", "rows_2p17"])
 def test_parallel_lookup_walk_matches_walk_kernels(ctx, sbn, monkeypatch, case):
