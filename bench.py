@@ -278,7 +278,7 @@ def main():
                     olanes = lanes_for(name)
                     obatch = batch if olanes == lanes else sbn.Batch(local, olanes)
                 ab = AirBench(sbn, torch, obatch, local, rank, name, 0)
-                osteps = max(4, args.steps // 2, olanes)   # at least one proof per lane
+                osteps = -(-max(4, args.steps // 2) // olanes) * olanes   # whole rounds of the lanes (a ragged last round runs almost alone)
                 ab.resident(0, olanes)
                 oms, _, _ = timed(ab.resident, 0, osteps)
                 ab.e2e(0, olanes)   # every lane's pinned staging arena exists before the timed region
