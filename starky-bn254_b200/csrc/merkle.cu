@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(128) k_leaf_hash(const u64* __restrict__ lde, 
 }
 
 // The same leaves with two lanes per permutation (poseidon_permute_pair): role 0 absorbs columns c .. c+5, role 1 columns c+6, c+7.
-// For trees of at most 2^14 leaves, where one thread per leaf leaves schedulers empty or with a single warp (tools/microbench,
-// 9 800 columns: 2^13 leaves 28.0 -> 16.5 ms, 2^14 leaves 28.4 -> 25.6 ms; from 2^15 leaves on the one-thread form is as fast).
+// For trees of at most 2^16 leaves, where one thread per leaf leaves schedulers empty or with few warps (tools/microbench:
+// 9 800 columns, 2^13 leaves 28.0 -> 16.5 ms, 2^14 leaves 28.4 -> 25.6 ms; 2^15 x 4 096 columns 19.7 -> 19.3 ms; 2^16 x 2 816 columns
+// 25.4 -> 23.1 ms; at 2^17 leaves the one-thread form is as fast or faster and stays).
 template <int BS> __global__ void __launch_bounds__(BS) k_leaf_hash_pair(const u64* __restrict__ lde, size_t col_stride, int ncols, int logn, int rate_bits,
                                                                          u64* __restrict__ digests, int sub_coset) {
   __shared__ PoseidonPairTables tab;
@@ -75,8 +76,9 @@ template <int BS> __global__ void __launch_bounds__(BS) k_leaf_hash_pair(const u
 }
 static void launch_leaf_hash(sbn_ctx* ctx, const u64* lde, size_t col_stride, size_t nleaves, int ncols, int logn, int rate_bits, u64* digests, int sub_coset) {
   const bool no_pair = getenv("SBN_LEAF_HASH_ONE_THREAD") != nullptr;   // test switch: always one thread per leaf
-  if (ncols > 4 && nleaves >= 16 && nleaves <= (size_t(1) << 14) && !no_pair) {
-    if (nleaves > (size_t(1) << 13)) k_leaf_hash_pair<256><<<(unsigned)((2 * nleaves + 255) / 256), 256, 0, ctx->stream>>>(lde, col_stride, ncols, logn, rate_bits, digests, sub_coset);
+  if (ncols > 4 && nleaves >= 16 && nleaves <= (size_t(1) << 16) && !no_pair) {
+    // block size by measurement (profiles/r02_poseidon_pair_microbench.txt): 256 threads for 2^14 .. 2^15 leaves, 128 otherwise
+    if (nleaves > (size_t(1) << 13) && nleaves <= (size_t(1) << 15)) k_leaf_hash_pair<256><<<(unsigned)((2 * nleaves + 255) / 256), 256, 0, ctx->stream>>>(lde, col_stride, ncols, logn, rate_bits, digests, sub_coset);
     else k_leaf_hash_pair<128><<<(unsigned)((2 * nleaves + 127) / 128), 128, 0, ctx->stream>>>(lde, col_stride, ncols, logn, rate_bits, digests, sub_coset);
   } else {
     k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, ctx->stream>>>(lde, col_stride, ncols, logn, rate_bits, digests, sub_coset);

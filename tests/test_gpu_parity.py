@@ -180,9 +180,9 @@ def test_parallel_lookup_walk_matches_walk_kernels(ctx, sbn, monkeypatch, case):
         assert (a == c).all()
 
 
-@pytest.mark.parametrize("air,n", [("ModularStark", 512), ("ModularStark", 8192), ("Fq12ExpStark", 2), ("Fq12ExpStark", 16)])
+@pytest.mark.parametrize("air,n", [("ModularStark", 512), ("ModularStark", 8192), ("ModularStark", 32768), ("Fq12ExpStark", 2), ("Fq12ExpStark", 16)])
 def test_leaf_hash_two_lanes_per_leaf_matches_one_thread_per_leaf(ctx, sbn, monkeypatch, air, n):
-    """Trees of at most 2^14 leaves are hashed with two lanes per permutation (k_leaf_hash_pair); SBN_LEAF_HASH_ONE_THREAD=1 forces the
+    """Trees of at most 2^16 leaves are hashed with two lanes per permutation (k_leaf_hash_pair); SBN_LEAF_HASH_ONE_THREAD=1 forces the
     one-thread-per-leaf kernel: same proof bytes (column counts with and without a ragged last chunk, 2^10 .. 2^14 leaves)."""
     stark = getattr(sbn, air)(n, ctx)
     gen = {"ModularStark": sbn.synthetic.modular_ios, "Fq12ExpStark": sbn.synthetic.fq12_exp_ios, "FqExpStark": sbn.synthetic.fq_exp_ios}[air]
