@@ -203,7 +203,11 @@ def main():
     sbn = entry.load_package()
     from starky_bn254_b200 import sharding
     stream = torch.cuda.current_stream()
-    host_threads = max(6, (os.cpu_count() or 16) // max(world, 1))   # one native host thread per lane and rank
+    try:
+        ncpu = len(os.sched_getaffinity(0))   # the cores this process may run on (cpuset-aware)
+    except AttributeError:
+        ncpu = os.cpu_count() or 16
+    host_threads = max(6, ncpu // max(world, 1))   # one native host thread per lane and rank
 
     def lanes_for(air):
         return max(1, args.inflight) if args.inflight else min(LANES[air], host_threads)
